@@ -1,0 +1,219 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (/root/reference).
+
+Run in the build container only (the GPU box has no reference checkout):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+Every fixture stores the inputs next to the reference's outputs, so the tests
+need neither the reference nor this script.  Quantities with an arbitrary
+phase / sign (eigenvectors, beamforming vectors, Watson modes) are stored as
+produced AND compared phase-invariantly by the tests.
+"""
+import os
+
+import numpy as np
+
+from . import ref_shim, synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                   'tests', 'golden')
+
+
+def _cacgmm_case(ref, name, y, init, iterations, **kw):
+    T = ref.distribution.CACGMMTrainer
+    model = T().fit(y, initialization=init, iterations=iterations, **kw)
+    aff, q = model.predict(
+        y, return_quadratic_form=True,
+        source_activity_mask=kw.get('source_activity_mask'))
+    out = dict(
+        y=y, init=init, iterations=iterations,
+        weight=model.weight,
+        eigenvectors=model.cacg.covariance_eigenvectors,
+        eigenvalues=model.cacg.covariance_eigenvalues,
+        covariance=model.cacg.covariance,
+        affiliation=aff, quadratic_form=q,
+        log_likelihood=model.log_likelihood(y),
+    )
+    for k, v in kw.items():
+        out['kw_' + k] = np.asarray(v if v is not False else 0)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    return model
+
+
+def make_cacgmm(ref):
+    # structured mixture, D=4 K=2 (config C1 scaled down)
+    y, _ = synth.structured_stft(6, 60, 4, 2, seed=1)
+    init = synth.init_affiliation(6, 2, 60, seed=7)
+    _cacgmm_case(ref, 'cacgmm_d4k2', y, init, 8)
+    # noise input, D=8 K=3 (config C2 scaled down)
+    y = synth.noise_stft(4, 70, 8, seed=0)
+    init = synth.init_affiliation(4, 3, 70, seed=7)
+    _cacgmm_case(ref, 'cacgmm_d8k3', y, init, 6)
+    # structured D=8 K=3: near-singular covariances, exercises the floor
+    y, _ = synth.structured_stft(3, 90, 8, 3, seed=2)
+    init = synth.init_affiliation(3, 3, 90, seed=3)
+    _cacgmm_case(ref, 'cacgmm_d8k3_structured', y, init, 10)
+    # option variants on a small D=3 K=2 problem (dims of the reference's tests)
+    y, _ = synth.structured_stft(3, 50, 3, 2, seed=5)
+    init = synth.init_affiliation(3, 2, 50, seed=11)
+    rng = np.random.RandomState(4)
+    sal = rng.uniform(0.1, 1.0, size=(3, 50))
+    sam = rng.uniform(size=(3, 2, 50)) > 0.2
+    sam[:, 0, :] |= ~sam[:, 1, :]  # at least one class active per frame
+    _cacgmm_case(ref, 'cacgmm_opt_saliency', y, init, 5, saliency=sal)
+    _cacgmm_case(ref, 'cacgmm_opt_mask', y, init, 5,
+                 source_activity_mask=sam)
+    _cacgmm_case(ref, 'cacgmm_opt_trace', y, init, 5, covariance_norm='trace')
+    _cacgmm_case(ref, 'cacgmm_opt_nonorm', y, init, 5, covariance_norm=False)
+    _cacgmm_case(ref, 'cacgmm_opt_w2', y, init, 5, weight_constant_axis=-2)
+    _cacgmm_case(ref, 'cacgmm_opt_eps0', y, init, 5, affiliation_eps=0.,
+                 eigenvalue_floor=1e-6)
+    # broadcast initialisation (singleton independent dim), cacgmm.py:221-228
+    _cacgmm_case(ref, 'cacgmm_opt_bcast', y, init[:1], 5)
+    # warm start from a model: 3 + 2 iterations, cacgmm.py:229-234
+    T = ref.distribution.CACGMMTrainer
+    m3 = T().fit(y, initialization=init, iterations=3)
+    m5 = T().fit(y, initialization=m3, iterations=2)
+    np.savez_compressed(
+        os.path.join(OUT, 'cacgmm_warm.npz'), y=y, init=init,
+        w3=m3.weight, V3=m3.cacg.covariance_eigenvectors,
+        l3=m3.cacg.covariance_eigenvalues,
+        w5=m5.weight, cov5=m5.cacg.covariance,
+        l5=m5.cacg.covariance_eigenvalues)
+
+
+def make_cacg_steps(ref):
+    """Single E / M step pieces on fixed model parameters."""
+    rng = np.random.RandomState(21)
+    F, K, D, T = 3, 3, 5, 40
+    y = synth.noise_stft(F, T, D, seed=9)
+    z = ref.cacg.normalize_observation(y)
+    cov = synth.pos_def_hermitian(F, K, D, D, seed=3)
+    m = ref.cacg.ComplexAngularCentralGaussian.from_covariance(
+        cov.copy(), eigenvalue_floor=1e-10)
+    log_pdf, q = m._log_pdf(z[..., None, :, :])
+    w = rng.uniform(size=(F, K, 1))
+    w /= w.sum(-2, keepdims=True)
+    aff = ref.mixture_model_utils.log_pdf_to_affiliation(
+        w, log_pdf, affiliation_eps=1e-10)
+    m2 = ref.cacg.ComplexAngularCentralGaussianTrainer()._fit(
+        z[..., None, :, :], aff, q)
+    np.savez_compressed(
+        os.path.join(OUT, 'cacg_steps.npz'), y=y, z=z, cov=cov,
+        V=m.covariance_eigenvectors, lam=m.covariance_eigenvalues,
+        log_pdf=log_pdf, q=q, w=w, aff=aff,
+        fit_cov=m2.covariance, fit_lam=m2.covariance_eigenvalues)
+
+
+def make_cwmm(ref):
+    T = ref.distribution.CWMMTrainer
+    cases = {
+        'cwmm_d6k4': (synth.structured_stft(4, 120, 6, 4, seed=6)[0], 4, 6),
+        'cwmm_d4k2': (synth.structured_stft(5, 80, 4, 2, seed=8)[0], 2, 7),
+    }
+    for name, (y, K, it) in cases.items():
+        F, N, D = y.shape
+        init = synth.init_affiliation(F, K, N, seed=13)
+        tr = T()
+        model = tr.fit(y, initialization=init, iterations=it)
+        aff = model.predict(y)
+        np.savez_compressed(
+            os.path.join(OUT, name + '.npz'), y=y, init=init, iterations=it,
+            weight=model.weight, mode=model.complex_watson.mode,
+            concentration=model.complex_watson.concentration,
+            affiliation=aff)
+    # the spline itself (the concentration look-up table is model state)
+    for D in (4, 6, 8):
+        tr = ref.complex_watson.ComplexWatsonTrainer(D)
+        lam = np.concatenate([
+            [0, 1 / D, 1 / D + 1e-4, 0.9599999, 1],
+            np.linspace(1 / D - 0.01, 1.0, 200)])
+        np.savez_compressed(
+            os.path.join(OUT, f'cw_spline_d{D}.npz'), D=D, lam=lam,
+            kappa=tr.hypergeometric_ratio_inverse(lam),
+            kappa_grid=np.linspace(0, 500, 101),
+            log_norm=ref.complex_watson.ComplexWatson.log_norm_1f1(
+                np.linspace(0, 500, 101), D))
+
+
+def make_permutation(ref):
+    pa = ref.permutation_alignment
+    rng = np.random.RandomState(31)
+    out = {}
+    # (a) default 512-point plan on a synthetic permuted mask, F=257
+    for tag, stft_size, K, T in (('a', 512, 3, 40), ('b', 1024, 2, 30)):
+        F = stft_size // 2 + 1
+        proto = rng.uniform(size=(K, 1, T)) ** 4
+        mask = proto + 0.35 * rng.uniform(size=(K, F, T))
+        mask /= mask.sum(0, keepdims=True)
+        perm = np.stack([rng.permutation(K) for _ in range(F)], axis=1)
+        mask = mask[perm, np.arange(F)]
+        al = pa.DHTVPermutationAlignment.from_stft_size(stft_size)
+        mapping = al.calculate_mapping(mask.copy())
+        out[f'{tag}_mask'] = mask
+        out[f'{tag}_plan'] = np.asarray(al.alignment_plan)
+        out[f'{tag}_mapping'] = mapping
+        out[f'{tag}_aligned'] = al.apply_mapping(mask, mapping)
+    # (c) custom small plan, K=4, pure noise mask (many near ties)
+    K, F, T = 4, 65, 25
+    mask = rng.uniform(size=(K, F, T))
+    mask /= mask.sum(0, keepdims=True)
+    al = pa.DHTVPermutationAlignment(
+        stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+        main_iterations=5, sub_iterations=2)
+    out['c_mask'] = mask
+    out['c_plan'] = np.asarray(al.alignment_plan)
+    out['c_mapping'] = al.calculate_mapping(mask.copy())
+    # greedy assignment known answer, permutation_alignment.py:475-508
+    sm = np.array([[11, 10, 0], [4, 5, 10], [6, 0, 5]])
+    out['score'] = sm
+    out['score_greedy'] = pa._mapping_from_score_matrix(sm, 'greedy')
+    np.savez_compressed(os.path.join(OUT, 'permutation.npz'), **out)
+
+
+def make_beamformer(ref):
+    bf = ref.beamformer
+    F, D, T, K = 9, 6, 80, 3
+    rng = np.random.RandomState(41)
+    Y = np.swapaxes(synth.structured_stft(F, T, D, K, seed=12)[0], -1, -2)
+    Y = np.ascontiguousarray(Y)
+    mask = rng.uniform(size=(F, K, T))
+    mask /= mask.sum(1, keepdims=True)
+    psd = bf.get_power_spectral_density_matrix(Y, mask)
+    psd_nonorm = bf.get_power_spectral_density_matrix(Y, mask,
+                                                      normalize=False)
+    psd_single = bf.get_power_spectral_density_matrix(Y, mask[:, 0])
+    psd_nomask = bf.get_power_spectral_density_matrix(Y)
+    target, noise = psd[:, 0], psd[:, 1] + psd[:, 2]
+    pca = bf.get_pca_vector(target)
+    mvdr = bf.get_mvdr_vector(pca, noise)
+    gev = bf._get_gev_vector(target, noise)
+    souden, ref_ch = bf.get_mvdr_vector_souden(target, noise,
+                                               return_ref_channel=True)
+    ban = bf.blind_analytic_normalization(gev, noise)
+    applied = bf.apply_beamforming_vector(gev, Y)
+    np.savez_compressed(
+        os.path.join(OUT, 'beamformer.npz'), Y=Y, mask=mask, psd=psd,
+        psd_nonorm=psd_nonorm, psd_single=psd_single, psd_nomask=psd_nomask,
+        target=target, noise=noise, pca=pca, mvdr=mvdr, gev=gev,
+        souden=souden, ref_channel=ref_ch, ban=ban, applied=applied)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    make_cacgmm(ref)
+    make_cacg_steps(ref)
+    make_cwmm(ref)
+    make_permutation(ref)
+    make_beamformer(ref)
+    total = 0
+    for n in sorted(os.listdir(OUT)):
+        s = os.path.getsize(os.path.join(OUT, n))
+        total += s
+        print(f'{n:36s} {s:8d} B')
+    print('total', total)
+
+
+if __name__ == '__main__':
+    main()
