@@ -1,0 +1,141 @@
+/* pb_bss_b200 C ABI -- the drop-in boundary of the pb_bss EM / beamforming hot path.
+ *
+ * pb_bss (the reference) is a pure NumPy library; its only native seam is the
+ * import-time hook around two Cython LAPACK loops
+ * (pb_bss/extraction/beamformer.py:38-56 ->
+ *  pb_bss/extraction/cythonized/get_gev_vector.pyx:42,
+ *  pb_bss/extraction/cythonized/c_eig.pyx:14).  This library moves the whole
+ * per-bin hot path behind one C ABI; each entry point names the reference
+ * function(s) it replaces.  A maintainer binds it with ctypes exactly like
+ * pb_bss_b200/_lib.py does.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (the library never
+ *    allocates persistent memory and never frees caller memory);
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered
+ *    and asynchronous, nothing here synchronises the device;
+ *  - return value: 0 = ok, -i = argument i (1-based) invalid (LAPACK INFO<0
+ *    convention, cf. get_gev_vector.pyx:130-147), > 0 = CUDA runtime error
+ *    code; pbb_last_error() gives the message (thread-local);
+ *  - numerical failures (non-finite covariance, not-positive-definite noise
+ *    PSD, ...) are reported through a caller-provided device status word
+ *    `int* status` (0 = ok, else 1 + index of the first failing matrix/bin),
+ *    which the caller reads after synchronising -- the reference raises
+ *    AssertionError / ValueError at the same places;
+ *  - all arithmetic is IEEE fp64; `dtype` only selects the STORAGE type of the
+ *    complex observation (PBB_C64 = float2, PBB_C128 = double2).
+ */
+#ifndef PBB_H_
+#define PBB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBB_C64 0
+#define PBB_C128 1
+
+/* covariance_norm of CACGMMTrainer.fit (pb_bss/distribution/cacgmm.py:152) */
+#define PBB_NORM_NONE 0       /* covariance_norm=False */
+#define PBB_NORM_EIGENVALUE 1 /* 'eigenvalue' (default) */
+#define PBB_NORM_TRACE 2      /* 'trace' */
+
+/* weight_constant_axis (pb_bss/distribution/mixture_model_utils.py:133-203) */
+#define PBB_WEIGHT_TIME 0     /* (-1,): one weight per (bin, class) */
+#define PBB_WEIGHT_CONST 1    /* -2: constant 1/K */
+
+const char* pbb_last_error(void);
+int pbb_version(void);
+
+/* ------------------------------------------------------------------------
+ * Observation normalisation.
+ * swap=1: pb_bss/distribution/complex_angular_central_gaussian.py:34-55
+ *         (unit norm over D, zero vectors stay zero, output (F, D, T));
+ * swap=0: pb_bss/distribution/complex_watson.py:16-29 (output (F, T, D)).
+ * y: (F, T, D) complex of `dtype`; z: same dtype. */
+int pbb_normalize_observation(const void* y, void* z, int F, int T, int D,
+                              int dtype, int swap, void* stream);
+
+/* ------------------------------------------------------------------------
+ * cACGMM (pb_bss/distribution/cacgmm.py).
+ *
+ * Device model of one fit: for every (bin f, class k)
+ *   eigenvectors (F, K, D, D) complex128 row-major, column e = e-th vector
+ *   eigenvalues  (F, K, D)    float64, ascending
+ *   weight       (F, K)       float64
+ * = CACGMM.weight / cacg.covariance_eigenvectors / covariance_eigenvalues
+ * (cacgmm.py:58-62, complex_angular_central_gaussian.py:78-79).
+ */
+typedef struct pbb_cacgmm_options {
+  int iterations;          /* > 0 */
+  int covariance_norm;     /* PBB_NORM_* */
+  int weight_mode;         /* PBB_WEIGHT_* */
+  int hermitize;           /* accepted for API parity; the scatter matrix is
+                              accumulated in Hermitian form either way */
+  double affiliation_eps;  /* clip of the posterior, cacgmm.py:154 */
+  double eigenvalue_floor; /* cacgmm.py:155 */
+  int frames_per_block;    /* 0 = library default; tuning knob */
+  int reserved;
+} pbb_cacgmm_options;
+
+/* Bytes of scratch pbb_cacgmm_fit / _predict need for this problem size. */
+size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K);
+
+/* CACGMMTrainer.fit (cacgmm.py:142-280): full EM loop on the device.
+ *  y            (F, T, D) complex `dtype`, un-normalised STFT
+ *  init_aff     (F, K, T) float64 initial affiliations, or NULL for a warm
+ *               start from the model already stored in
+ *               eigenvectors/eigenvalues/weight (cacgmm.py:229-234)
+ *  saliency     (F, T) float64 or NULL
+ *  activity     (F, K, T) uint8 source_activity_mask or NULL
+ *  outputs      eigenvectors, eigenvalues, weight as described above
+ *  status       device int, see header comment
+ */
+int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K,
+                   const double* init_aff, const double* saliency,
+                   const uint8_t* activity, const pbb_cacgmm_options* opt,
+                   void* eigenvectors, double* eigenvalues, double* weight,
+                   void* workspace, size_t workspace_bytes, int* status,
+                   void* stream);
+
+/* CACGMM.predict / _predict / log_likelihood (cacgmm.py:64-138): one E-step.
+ *  affiliation  (F, K, T) float64 out (may be NULL)
+ *  quadratic    (F, K, T) float64 out (may be NULL)
+ *  loglik       (F) float64 out, per-bin sum_t logsumexp_k log_pdf (may be NULL)
+ *  affiliation_eps: 0 for predict (cacgmm.py:73)
+ */
+int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K,
+                       const void* eigenvectors, const double* eigenvalues,
+                       const double* weight, int weight_mode,
+                       const uint8_t* activity, double affiliation_eps,
+                       double* affiliation, double* quadratic, double* loglik,
+                       void* workspace, size_t workspace_bytes, int* status,
+                       void* stream);
+
+/* One M-step from given affiliations and quadratic forms:
+ * CACGMMTrainer._m_step (cacgmm.py:315-345) =
+ * estimate_mixture_weight + ComplexAngularCentralGaussianTrainer._fit
+ * (complex_angular_central_gaussian.py:253-342) + from_covariance (:81-132).
+ *  quadratic may be NULL (= ones, the first iteration, cacgmm.py:210). */
+int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K,
+                     const double* affiliation, const double* quadratic,
+                     const double* saliency, const pbb_cacgmm_options* opt,
+                     void* eigenvectors, double* eigenvalues, double* weight,
+                     void* workspace, size_t workspace_bytes, int* status,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * Batched Hermitian eigendecomposition, ascending eigenvalues
+ * (np.linalg.eigh as used in complex_angular_central_gaussian.py:95 and
+ * pb_bss/utils.py:154).  a: (n, D, D) complex128 (only read), w: (n, D),
+ * v: (n, D, D) complex128, columns are eigenvectors. */
+int pbb_heig_batched(const void* a, int n, int D, double* w, void* v,
+                     int* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBB_H_ */

@@ -1,0 +1,84 @@
+"""torch tensors as device-memory containers for the C ABI.
+
+Nothing here computes: tensors are allocated, copied host<->device and handed
+to the library as raw pointers on torch's current CUDA stream.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            'pb_bss_b200 needs a CUDA device (B200, sm_100a); there is no CPU '
+            'fallback. torch.cuda.is_available() is False.')
+
+
+def device():
+    require_cuda()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def is_tensor(x):
+    return isinstance(x, torch.Tensor)
+
+
+def to_device(x, dtype=None):
+    """numpy array / torch tensor -> contiguous CUDA tensor (copy only if needed)."""
+    dev = device()
+    if not is_tensor(x):
+        x = np.asarray(x)
+        if not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x)
+        if not x.flags.writeable:
+            x = x.copy()
+        x = torch.from_numpy(x)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if x.device != dev:
+        x = x.to(dev, non_blocking=True)
+    return x.contiguous()
+
+
+def complex_dtype_code(t):
+    if t.dtype == torch.complex128:
+        return _lib.PBB_C128
+    if t.dtype == torch.complex64:
+        return _lib.PBB_C64
+    raise AssertionError(f'complex input required, got {t.dtype}')
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+def to_host(t, like_numpy):
+    """Returns numpy if the caller passed numpy, else the tensor itself."""
+    if like_numpy:
+        return t.cpu().numpy()
+    return t
+
+
+_workspaces = {}
+
+
+def workspace(nbytes):
+    """A cached uint8 scratch tensor of at least nbytes on the current device
+    (the caller of the C ABI owns all memory, include/pbb.h)."""
+    dev = device()
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws

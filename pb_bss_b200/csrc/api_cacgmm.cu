@@ -1,0 +1,369 @@
+// C-ABI entry points for the cACGMM EM path (see include/pbb.h).
+#include <cstdarg>
+#include <cstring>
+
+#include "em_kernels.cuh"
+
+namespace pbb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// out[r] = sum_c in[r * n + c], fixed order
+__global__ void sum_rows_kernel(const double* in, double* out, int rows, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int c = 0; c < n; ++c) s += in[(size_t)r * n + c];
+  out[r] = s;
+}
+
+// ---- workspace carving -------------------------------------------------------
+struct CacgmmWorkspace {
+  void* z;
+  double* part;
+  double* coef;
+  double* ld;
+  double* w;
+  double* ew;
+  double* loglik_part;
+  size_t bytes;
+};
+
+static int max_chunks(int T) { return (T + 31) / 32; }
+
+static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
+  CacgmmWorkspace ws;
+  const size_t NS = (size_t)D * D;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += align_up(n); return o; };
+  const size_t o_z = take((size_t)F * D * T * sizeof(double2));
+  const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
+  const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
+  const size_t o_ld = take((size_t)F * K * sizeof(double));
+  const size_t o_w = take((size_t)F * K * sizeof(double));
+  const size_t o_ew = take((size_t)F * K * sizeof(double));
+  const size_t o_ll = take((size_t)F * max_chunks(T) * sizeof(double));
+  char* b = reinterpret_cast<char*>(base);
+  ws.z = b + o_z;
+  ws.part = reinterpret_cast<double*>(b + o_part);
+  ws.coef = reinterpret_cast<double*>(b + o_coef);
+  ws.ld = reinterpret_cast<double*>(b + o_ld);
+  ws.w = reinterpret_cast<double*>(b + o_w);
+  ws.ew = reinterpret_cast<double*>(b + o_ew);
+  ws.loglik_part = reinterpret_cast<double*>(b + o_ll);
+  ws.bytes = off;
+  return ws;
+}
+
+// ---- launches ------------------------------------------------------------------
+template <typename CT>
+static int launch_normalize(const void* y, void* z, int F, int T, int D, int swap, cudaStream_t st) {
+  const int block = D <= 16 ? 128 : 32;
+  dim3 grid((T + block - 1) / block, F);
+  const size_t smem = (size_t)block * (D + 1) * sizeof(double2);
+  normalize_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T,
+                                                    D, swap);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool fast_shape(int D, int K) { return (D == 4 || D == 6 || D == 8) && K >= 2 && K <= 4; }
+
+template <int D, int K>
+static cudaError_t launch_fast_dk(const EmArgs& a, int dtype, cudaStream_t st) {
+  dim3 grid(a.nch, a.F);
+  if (dtype == PBB_C128) em_fast_kernel<D, K, double2><<<grid, 32 * kEmGroups, 0, st>>>(a);
+  else em_fast_kernel<D, K, float2><<<grid, 32 * kEmGroups, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_fast_d(const EmArgs& a, int dtype, cudaStream_t st) {
+  switch (a.K) {
+    case 2: return launch_fast_dk<D, 2>(a, dtype, st);
+    case 3: return launch_fast_dk<D, 3>(a, dtype, st);
+    default: return launch_fast_dk<D, 4>(a, dtype, st);
+  }
+}
+
+// Fills nch / frames_per_block and launches the EM kernel for the shape.
+static int launch_em(EmArgs a, int dtype, int frames_per_block, cudaStream_t st) {
+  if (fast_shape(a.D, a.K)) {
+    int fpb = frames_per_block > 0 ? frames_per_block : 128;
+    fpb = (fpb + 31) / 32 * 32;
+    if (fpb > (a.T + 31) / 32 * 32) fpb = (a.T + 31) / 32 * 32;
+    a.frames_per_block = fpb;
+    a.nch = (a.T + fpb - 1) / fpb;
+    cudaError_t e;
+    switch (a.D) {
+      case 4: e = launch_fast_d<4>(a, dtype, st); break;
+      case 6: e = launch_fast_d<6>(a, dtype, st); break;
+      default: e = launch_fast_d<8>(a, dtype, st); break;
+    }
+    PBB_CUDA(e);
+    return a.nch;
+  }
+  a.frames_per_block = kGenFrames;
+  a.nch = (a.T + kGenFrames - 1) / kGenFrames;
+  a.softmax_fast = 0;
+  dim3 grid(a.nch, a.F);
+  const size_t smem = (size_t)2 * a.K * kGenFrames * sizeof(double) + (size_t)a.D * a.D * sizeof(int);
+  if (dtype == PBB_C128) {
+    PBB_CUDA(cudaFuncSetAttribute(em_generic_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    em_generic_kernel<double2><<<grid, kGenFrames, smem, st>>>(a);
+  } else {
+    PBB_CUDA(cudaFuncSetAttribute(em_generic_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    em_generic_kernel<float2><<<grid, kGenFrames, smem, st>>>(a);
+  }
+  PBB_CUDA(cudaGetLastError());
+  return a.nch;
+}
+
+static int update_warps(int D, int K) {
+  const size_t per = update_smem_per_warp(D);
+  int w = (int)((size_t)(200 * 1024) / per);
+  if (w > K) w = K;
+  if (w > 16) w = 16;
+  if (w < 1) w = 1;
+  return w;
+}
+
+static int launch_update(UpdArgs u, cudaStream_t st) {
+  u.warps = update_warps(u.D, u.K);
+  const size_t smem = update_smem_per_warp(u.D) * u.warps + (size_t)2 * u.K * sizeof(double) +
+                      (size_t)u.D * u.D * sizeof(int);
+  PBB_CUDA(cudaFuncSetAttribute(cacg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const int threads = 32 * u.warps < u.K ? ((u.K + 31) / 32 * 32) : 32 * u.warps;
+  cacg_update_kernel<<<u.F, threads, smem, st>>>(u);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
+  const size_t per = from_eig_smem_per_warp(u.D);
+  int w = (int)((size_t)(200 * 1024) / per);
+  if (w > u.K) w = u.K;
+  if (w > 16) w = 16;
+  u.warps = w;
+  const size_t smem = per * w + (size_t)u.K * sizeof(double) + (size_t)u.D * u.D * sizeof(int);
+  PBB_CUDA(cudaFuncSetAttribute(cacg_from_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const int threads = 32 * w < u.K ? ((u.K + 31) / 32 * 32) : 32 * w;
+  cacg_from_eig_kernel<<<u.F, threads, smem, st>>>(u);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool softmax_fast_ok(int D, const pbb_cacgmm_options* o) {
+  if (o->covariance_norm != PBB_NORM_EIGENVALUE) return false;
+  if (!(o->eigenvalue_floor > 0.0) || o->eigenvalue_floor > 1.0) return false;
+  return 2.0 * D * log10(1.0 / o->eigenvalue_floor) < 280.0;
+}
+
+static int check_shape(int F, int T, int D, int K, int dtype) {
+  PBB_CHECK_ARG(dtype == PBB_C64 || dtype == PBB_C128, 2, "dtype must be PBB_C64 or PBB_C128");
+  PBB_CHECK_ARG(F > 0, 3, "F must be positive");
+  PBB_CHECK_ARG(T > 0, 4, "T must be positive");
+  PBB_CHECK_ARG(D > 1 && D < 35, 5, "need 1 < D < 35 (cacgmm.py:197,250)");
+  PBB_CHECK_ARG(K > 0 && K < kMaxK, 6, "need 0 < K < 20 (cacgmm.py:249)");
+  return 0;
+}
+
+}  // namespace pbb
+
+using namespace pbb;
+
+extern "C" {
+
+const char* pbb_last_error(void) { return g_err; }
+int pbb_version(void) { return 100; }
+
+int pbb_normalize_observation(const void* y, void* z, int F, int T, int D, int dtype, int swap, void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  PBB_CHECK_ARG(z != nullptr, 2, "z is null");
+  PBB_CHECK_ARG(F > 0 && T > 0, 3, "empty shape");
+  PBB_CHECK_ARG(D > 0 && D < 256, 5, "bad D");
+  PBB_CHECK_ARG(dtype == PBB_C64 || dtype == PBB_C128, 6, "bad dtype");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == PBB_C128 ? launch_normalize<double2>(y, z, F, T, D, swap, st)
+                           : launch_normalize<float2>(y, z, F, T, D, swap, st);
+}
+
+size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K) {
+  if (F <= 0 || T <= 0 || D <= 0 || K <= 0) return 0;
+  return carve(nullptr, F, T, D, K).bytes;
+}
+
+int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const double* init_aff,
+                   const double* saliency, const uint8_t* activity, const pbb_cacgmm_options* opt,
+                   void* eigenvectors, double* eigenvalues, double* weight, void* workspace,
+                   size_t workspace_bytes, int* status, void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  if (int r = check_shape(F, T, D, K, dtype)) return r;
+  PBB_CHECK_ARG(opt != nullptr, 10, "options are null");
+  PBB_CHECK_ARG(opt->iterations > 0, 10, "iterations must be positive (cacgmm.py:200)");
+  PBB_CHECK_ARG(opt->covariance_norm >= 0 && opt->covariance_norm <= 2, 10, "bad covariance_norm");
+  PBB_CHECK_ARG(opt->weight_mode == PBB_WEIGHT_TIME || opt->weight_mode == PBB_WEIGHT_CONST, 10, "bad weight_mode");
+  PBB_CHECK_ARG(eigenvectors && eigenvalues && weight, 11, "model output is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 14,
+                "workspace too small (pbb_cacgmm_workspace_bytes)");
+  PBB_CHECK_ARG(status != nullptr, 16, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CacgmmWorkspace ws = carve(workspace, F, T, D, K);
+  PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  if (r) return r;
+
+  EmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
+  a.activity = activity; a.aff_eps = opt->affiliation_eps;
+  a.saliency = saliency; a.part = ws.part;
+
+  UpdArgs u;
+  memset(&u, 0, sizeof(u));
+  u.F = F; u.T = T; u.D = D; u.K = K;
+  u.part = ws.part;
+  u.covariance_norm = opt->covariance_norm;
+  u.weight_mode = opt->weight_mode;
+  u.has_saliency = saliency != nullptr;
+  u.eigenvalue_floor = opt->eigenvalue_floor;
+  u.evec = reinterpret_cast<double2*>(eigenvectors);
+  u.eval = eigenvalues; u.weight = weight;
+  u.coef = ws.coef; u.ld = ws.ld; u.ew = ws.ew;
+  u.status = status;
+
+  const bool fast_sm = softmax_fast_ok(D, opt);
+  int it = 0;
+  if (init_aff != nullptr) {
+    // iteration 0: M-step from the initial affiliations, q = 1 (cacgmm.py:206-228,269)
+    a.mode = kModeM; a.aff_in = init_aff; a.q_in = nullptr;
+    int nch = launch_em(a, dtype, opt->frames_per_block, st);
+    if (nch <= 0) return nch ? nch : 1;
+    u.nch = nch;
+    if ((r = launch_update(u, st))) return r;
+    it = 1;
+  } else {
+    // warm start: the model in the output arrays drives the first E-step (cacgmm.py:229-234)
+    FromEigArgs fe;
+    fe.F = F; fe.D = D; fe.K = K;
+    fe.evec = reinterpret_cast<const double2*>(eigenvectors);
+    fe.eval = eigenvalues; fe.weight = weight;
+    fe.coef = ws.coef; fe.ld = ws.ld; fe.w = ws.w; fe.ew = ws.ew;
+    if ((r = launch_from_eig(fe, st))) return r;
+  }
+  // the update kernel writes the E-step weights into `weight`; the E-step reads them from there
+  a.w = weight;
+  for (; it < opt->iterations; ++it) {
+    a.mode = kModeEM;
+    // a user-supplied model gives no bound on q / log det: keep the log-domain softmax for its E-step
+    a.softmax_fast = (fast_sm && !(init_aff == nullptr && it == 0)) ? 1 : 0;
+    if (init_aff == nullptr && it == 0) a.w = ws.w;
+    int nch = launch_em(a, dtype, opt->frames_per_block, st);
+    if (nch <= 0) return nch ? nch : 1;
+    a.w = weight;
+    u.nch = nch;
+    if ((r = launch_update(u, st))) return r;
+  }
+  return 0;
+}
+
+int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K, const void* eigenvectors,
+                       const double* eigenvalues, const double* weight, int weight_mode,
+                       const uint8_t* activity, double affiliation_eps, double* affiliation, double* quadratic,
+                       double* loglik, void* workspace, size_t workspace_bytes, int* status, void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  if (int r = check_shape(F, T, D, K, dtype)) return r;
+  PBB_CHECK_ARG(eigenvectors && eigenvalues, 7, "model is null");
+  PBB_CHECK_ARG(weight != nullptr || weight_mode == PBB_WEIGHT_CONST, 9, "weight is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 16,
+                "workspace too small (pbb_cacgmm_workspace_bytes)");
+  PBB_CHECK_ARG(status != nullptr, 18, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CacgmmWorkspace ws = carve(workspace, F, T, D, K);
+  PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  if (r) return r;
+  FromEigArgs fe;
+  fe.F = F; fe.D = D; fe.K = K;
+  fe.evec = reinterpret_cast<const double2*>(eigenvectors);
+  fe.eval = eigenvalues;
+  fe.weight = weight_mode == PBB_WEIGHT_CONST ? nullptr : weight;
+  fe.coef = ws.coef; fe.ld = ws.ld; fe.w = ws.w; fe.ew = ws.ew;
+  if ((r = launch_from_eig(fe, st))) return r;
+  EmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.mode = kModeE; a.softmax_fast = 0;
+  a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
+  a.activity = activity; a.aff_eps = affiliation_eps;
+  a.aff_out = affiliation; a.q_out = quadratic;
+  a.loglik_part = loglik ? ws.loglik_part : nullptr;
+  int nch = launch_em(a, dtype, 0, st);
+  if (nch <= 0) return nch ? nch : 1;
+  if (loglik) {
+    // per-bin sum of the chunk partials, fixed order
+    sum_rows_kernel<<<(F + 127) / 128, 128, 0, st>>>(ws.loglik_part, loglik, F, nch);
+    PBB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K, const double* affiliation,
+                     const double* quadratic, const double* saliency, const pbb_cacgmm_options* opt,
+                     void* eigenvectors, double* eigenvalues, double* weight, void* workspace,
+                     size_t workspace_bytes, int* status, void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  if (int r = check_shape(F, T, D, K, dtype)) return r;
+  PBB_CHECK_ARG(affiliation != nullptr, 7, "affiliation is null");
+  PBB_CHECK_ARG(opt != nullptr, 10, "options are null");
+  PBB_CHECK_ARG(eigenvectors && eigenvalues && weight, 11, "model output is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 14,
+                "workspace too small (pbb_cacgmm_workspace_bytes)");
+  PBB_CHECK_ARG(status != nullptr, 16, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CacgmmWorkspace ws = carve(workspace, F, T, D, K);
+  PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  if (r) return r;
+  EmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.mode = kModeM; a.aff_in = affiliation; a.q_in = quadratic;
+  a.saliency = saliency; a.part = ws.part;
+  int nch = launch_em(a, dtype, opt->frames_per_block, st);
+  if (nch <= 0) return nch ? nch : 1;
+  UpdArgs u;
+  memset(&u, 0, sizeof(u));
+  u.F = F; u.T = T; u.D = D; u.K = K; u.nch = nch;
+  u.part = ws.part;
+  u.covariance_norm = opt->covariance_norm;
+  u.weight_mode = opt->weight_mode;
+  u.has_saliency = saliency != nullptr;
+  u.eigenvalue_floor = opt->eigenvalue_floor;
+  u.evec = reinterpret_cast<double2*>(eigenvectors);
+  u.eval = eigenvalues; u.weight = weight;
+  u.coef = ws.coef; u.ld = ws.ld; u.ew = ws.ew;
+  u.status = status;
+  return launch_update(u, st);
+}
+
+}  // extern "C"
+

@@ -1,0 +1,141 @@
+// Warp-cooperative complex Hermitian eigensolver (parallel-order cyclic Jacobi).
+//
+// One warp diagonalises one D x D Hermitian matrix held in shared memory.
+// Each round applies D/2 disjoint plane rotations (round-robin tournament
+// ordering), so a sweep is D-1 rounds of fully parallel row/column updates.
+// The rotation test |a_pq|^2 <= eps^2 |a_pp a_qq| gives the high relative
+// accuracy Jacobi is known for on positive definite matrices, which matters
+// here because 1/lambda of near-singular speech covariances feeds the E-step.
+//
+// Replaces np.linalg.eigh at pb_bss/distribution/complex_angular_central_gaussian.py:95,
+// pb_bss/utils.py:154 and (after a Cholesky reduction) scipy.linalg.eigh(a, b) /
+// LAPACK zhegvd at pb_bss/extraction/cythonized/get_gev_vector.pyx:124.
+#pragma once
+#include "common.cuh"
+
+namespace pbb {
+
+constexpr int kJacobiMaxSweeps = 40;
+
+// shared memory a warp needs: A (D*D double2) + V (D*D double2) + rot ((D+1)/2 * 6 doubles)
+__host__ __device__ inline size_t jacobi_smem_bytes(int D) {
+  return (size_t)2 * D * D * sizeof(double2) + (size_t)((D + 1) / 2) * 6 * sizeof(double);
+}
+
+// In: A Hermitian (row-major, ld = D) in shared memory.  Out: A diagonal holds
+// the eigenvalues (unsorted), V the eigenvectors as columns.  If `V_init` is
+// true V is taken as given (and must be consistent with A = V0^H A0 V0, the
+// warm start); otherwise V is set to the identity.  Returns the number of
+// sweeps used.  All 32 lanes must call.
+__device__ inline int warp_jacobi(double2* __restrict__ A, double2* __restrict__ V,
+                                  double* __restrict__ rot, int D, int lane, bool V_init = false) {
+  const int n = D + (D & 1);  // tournament size (a dummy player for odd D)
+  const int npair = n / 2;
+  const double eps2 = DBL_EPSILON * DBL_EPSILON;
+  if (!V_init) {
+    for (int i = lane; i < D * D; i += 32) V[i] = make_double2((i / D == i % D) ? 1.0 : 0.0, 0.0);
+  }
+  __syncwarp();
+  int sweep = 0;
+  for (; sweep < kJacobiMaxSweeps; ++sweep) {
+    unsigned rotated = 0;
+    for (int r = 0; r < n - 1; ++r) {
+      // ---- (a) rotation parameters, one lane per pair -----------------------
+      bool act = false;
+      if (lane < npair) {
+        const int m = n - 1;
+        int p, q;
+        if (lane == 0) { p = r % m; q = n - 1; }
+        else { p = (r + lane) % m; q = (r - lane + m) % m; }
+        if (p > q) { int t = p; p = q; q = t; }
+        double c = 1.0, sr = 0.0, si = 0.0, an = 0.0, dn = 0.0;
+        if (q < D) {
+          const double a = A[p * D + p].x, d = A[q * D + q].x;
+          const double2 b = A[p * D + q];
+          const double m2 = b.x * b.x + b.y * b.y;
+          if (m2 > eps2 * fabs(a * d) && m2 > 1e-300) {
+            act = true;
+            const double dl = 0.5 * (d - a);
+            const double sg = dl >= 0.0 ? 1.0 : -1.0;
+            const double h = fabs(dl) + sqrt(dl * dl + m2);
+            const double w = rsqrt(h * h + m2);
+            c = h * w;
+            sr = sg * b.x * w;
+            si = sg * b.y * w;
+            const double tb = sg * m2 / h;
+            an = a - tb;
+            dn = d + tb;
+          }
+        }
+        double* ro = rot + lane * 6;
+        ro[0] = c; ro[1] = sr; ro[2] = si; ro[3] = an; ro[4] = dn;
+        ro[5] = act ? (double)(p | (q << 8)) : -1.0;  // packed pair or "inactive"
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, act);
+      rotated |= any;
+      __syncwarp();
+      if (any == 0) continue;
+      // ---- (b) column updates of A and V: X <- X J ---------------------------
+      for (int task = lane; task < npair * D * 2; task += 32) {
+        const int pi = task / (2 * D);
+        const int rem = task - pi * 2 * D;
+        const double* ro = rot + pi * 6;
+        if (ro[5] < 0.0) continue;
+        const int pq = (int)ro[5];
+        const int p = pq & 255, q = pq >> 8;
+        double2* X = rem < D ? A : V;
+        const int i = rem < D ? rem : rem - D;
+        const double c = ro[0], sr = ro[1], si = ro[2];
+        const double2 xp = X[i * D + p], xq = X[i * D + q];
+        // x_p' = c x_p - conj(s) x_q ; x_q' = s x_p + c x_q
+        X[i * D + p] = make_double2(c * xp.x - (sr * xq.x + si * xq.y), c * xp.y - (sr * xq.y - si * xq.x));
+        X[i * D + q] = make_double2(c * xq.x + (sr * xp.x - si * xp.y), c * xq.y + (sr * xp.y + si * xp.x));
+      }
+      __syncwarp();
+      // ---- (c) row updates of A: A <- J^H A ----------------------------------
+      for (int task = lane; task < npair * D; task += 32) {
+        const int pi = task / D;
+        const int j = task - pi * D;
+        const double* ro = rot + pi * 6;
+        if (ro[5] < 0.0) continue;
+        const int pq = (int)ro[5];
+        const int p = pq & 255, q = pq >> 8;
+        const double c = ro[0], sr = ro[1], si = ro[2];
+        const double2 ap = A[p * D + j], aq = A[q * D + j];
+        // a_p' = c a_p - s a_q ; a_q' = conj(s) a_p + c a_q
+        A[p * D + j] = make_double2(c * ap.x - (sr * aq.x - si * aq.y), c * ap.y - (sr * aq.y + si * aq.x));
+        A[q * D + j] = make_double2(c * aq.x + (sr * ap.x + si * ap.y), c * aq.y + (sr * ap.y - si * ap.x));
+      }
+      __syncwarp();
+      // ---- exact values for the rotated 2x2 blocks ---------------------------
+      if (lane < npair) {
+        const double* ro = rot + lane * 6;
+        if (ro[5] >= 0.0) {
+          const int pq = (int)ro[5];
+          const int p = pq & 255, q = pq >> 8;
+          A[p * D + q] = make_double2(0.0, 0.0);
+          A[q * D + p] = make_double2(0.0, 0.0);
+          A[p * D + p] = make_double2(ro[3], 0.0);
+          A[q * D + q] = make_double2(ro[4], 0.0);
+        }
+      }
+      __syncwarp();
+    }
+    if (rotated == 0) break;
+  }
+  return sweep + 1;
+}
+
+// rank of eigenvalue i in ascending order (stable), for i < D; lanes >= D get -1.
+// For D > 32 callers loop (i = lane, lane + 32, ...).
+__device__ inline int eig_rank(const double2* A, int D, int i) {
+  const double li = A[i * D + i].x;
+  int rank = 0;
+  for (int j = 0; j < D; ++j) {
+    const double lj = A[j * D + j].x;
+    rank += (lj < li) || (lj == li && j < i);
+  }
+  return rank;
+}
+
+}  // namespace pbb

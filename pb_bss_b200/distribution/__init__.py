@@ -1,0 +1,6 @@
+"""Mixture-model trainers of the hot path (pb_bss/distribution/__init__.py)."""
+from .complex_angular_central_gaussian import (  # noqa: F401
+    ComplexAngularCentralGaussian,
+    normalize_observation,
+)
+from .cacgmm import CACGMM, CACGMMTrainer  # noqa: F401

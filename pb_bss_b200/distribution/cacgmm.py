@@ -1,0 +1,337 @@
+"""cACGMM: ``CACGMMTrainer.fit / fit_predict`` and ``CACGMM.predict /
+log_likelihood`` with the signatures of pb_bss/distribution/cacgmm.py, executed
+by the CUDA kernels behind ``pbb_cacgmm_fit`` / ``pbb_cacgmm_predict``.
+
+numpy in -> numpy out (host buffers, copies included); CUDA tensors in -> CUDA
+tensors out (everything stays resident in HBM).
+"""
+import ctypes
+from dataclasses import dataclass, field
+from operator import xor
+
+import numpy as np
+import torch
+
+from .. import _device, _lib
+from .complex_angular_central_gaussian import (
+    ComplexAngularCentralGaussian,
+    normalize_observation,
+)
+from .utils import _ProbabilisticModel
+
+__all__ = ['CACGMM', 'CACGMMTrainer', 'normalize_observation']
+
+_NORMS = {'eigenvalue': _lib.NORM_EIGENVALUE, 'trace': _lib.NORM_TRACE,
+          False: _lib.NORM_NONE}
+
+
+def _weight_mode(weight_constant_axis, ndim):
+    """Maps ``weight_constant_axis`` (mixture_model_utils.py:133-203) onto the
+    modes the kernels implement; ``ndim`` is the affiliation rank."""
+    if isinstance(weight_constant_axis, list):
+        weight_constant_axis = tuple(weight_constant_axis)
+    if isinstance(weight_constant_axis, int):
+        ax = weight_constant_axis % ndim - ndim
+        if ax == -2:
+            return _lib.WEIGHT_CONST  # constant 1/K, shape (K, 1)
+        axes = (ax,)
+    else:
+        axes = tuple(a % ndim - ndim for a in weight_constant_axis)
+    if axes == (-1,):
+        return _lib.WEIGHT_TIME
+    raise NotImplementedError(
+        f'weight_constant_axis={weight_constant_axis!r}: only (-1,) and -2 run '
+        'on the device so far; frequency-tied weights couple the bins '
+        '(SURVEY.md section 8f, rank 2).')
+
+
+def _flatten_obs(y):
+    *independent, N, D = y.shape
+    F = int(np.prod(independent)) if independent else 1
+    return tuple(independent), F, N, D
+
+
+def _status_check(status, what):
+    s = int(status.item())  # synchronises the stream
+    if s != 0:
+        # the reference asserts finiteness at cacg.py:127,326,333
+        raise AssertionError(
+            f'{what}: non-finite covariance / eigenvalues in bin {s - 1}')
+
+
+@dataclass
+class CACGMM(_ProbabilisticModel):
+    weight: np.array = None  # (..., K, 1), or (K, 1) for weight_constant_axis=-2
+    cacg: ComplexAngularCentralGaussian = field(
+        default_factory=ComplexAngularCentralGaussian)
+
+    # -- device views of the model ------------------------------------------------
+    def _device_model(self, independent, F):
+        V = _device.to_device(self.cacg.covariance_eigenvectors, torch.complex128)
+        lam = _device.to_device(self.cacg.covariance_eigenvalues, torch.float64)
+        K, D = V.shape[-3], V.shape[-1]
+        V = V.expand(*independent, K, D, D).reshape(F, K, D, D).contiguous()
+        lam = lam.expand(*independent, K, D).reshape(F, K, D).contiguous()
+        w = _device.to_device(self.weight, torch.float64)
+        assert w.shape[-1] == 1, (
+            'time-varying weights (weight_constant_axis=-3) are not supported '
+            'on the device yet', tuple(w.shape))
+        w = w[..., 0].expand(*independent, K).reshape(F, K).contiguous()
+        return V, lam, w, K
+
+    def _run_predict(self, y, source_activity_mask, affiliation_eps,
+                     want_aff=True, want_q=False, want_ll=False):
+        like_numpy = not _device.is_tensor(y)
+        yd = _device.to_device(y)
+        code = _device.complex_dtype_code(yd)
+        independent, F, N, D = _flatten_obs(yd)
+        V, lam, w, K = self._device_model(independent, F)
+        assert V.shape[-1] == D, (V.shape, D)
+        act = None
+        if source_activity_mask is not None:
+            assert source_activity_mask.dtype in (bool, np.bool_, torch.bool), source_activity_mask.dtype
+            act = _device.to_device(source_activity_mask).to(torch.uint8)
+            act = act.expand(*independent, K, N).reshape(F, K, N).contiguous()
+        aff = _device.empty((F, K, N), torch.float64) if want_aff else None
+        q = _device.empty((F, K, N), torch.float64) if want_q else None
+        ll = _device.empty((F,), torch.float64) if want_ll else None
+        status = _device.empty((1,), torch.int32)
+        lib = _lib.load()
+        nbytes = lib.pbb_cacgmm_workspace_bytes(F, N, D, K)
+        ws = _device.workspace(nbytes)
+        _lib.check(lib.pbb_cacgmm_predict(
+            _device.ptr(yd), code, F, N, D, K, _device.ptr(V), _device.ptr(lam),
+            _device.ptr(w), _lib.WEIGHT_TIME, _device.ptr(act),
+            float(affiliation_eps), _device.ptr(aff), _device.ptr(q),
+            _device.ptr(ll), _device.ptr(ws), nbytes, _device.ptr(status),
+            _device.stream_ptr()), 'pbb_cacgmm_predict')
+        _status_check(status, 'CACGMM.predict')
+        shape = (*independent, K, N)
+        if aff is not None:
+            aff = _device.to_host(aff.reshape(shape), like_numpy)
+        if q is not None:
+            q = _device.to_host(q.reshape(shape), like_numpy)
+        return aff, q, ll, like_numpy
+
+    def predict(self, y, return_quadratic_form=False, source_activity_mask=None):
+        """Posterior affiliations (..., K, N) for observations y (..., N, D).
+
+        cacgmm.py:64-71: normalise, one E-step, affiliation_eps = 0."""
+        aff, q, _, _ = self._run_predict(y, source_activity_mask, 0.,
+                                         want_q=return_quadratic_form)
+        return (aff, q) if return_quadratic_form else aff
+
+    def log_likelihood(self, y):
+        """sum_{f,t} logsumexp_k log_pdf (without weights), cacgmm.py:97-138."""
+        _, _, ll, like_numpy = self._run_predict(y, None, 0., want_aff=False,
+                                                 want_ll=True)
+        total = ll.sum()
+        return np.float64(total.item()) if like_numpy else total
+
+
+class CACGMMTrainer:
+    def fit(
+            self,
+            y,
+            initialization=None,
+            num_classes=None,
+            iterations=100,
+            *,
+            saliency=None,
+            source_activity_mask=None,
+            weight_constant_axis=(-1,),
+            hermitize=True,
+            covariance_norm='eigenvalue',
+            affiliation_eps=1e-10,
+            eigenvalue_floor=1e-10,
+            inline_permutation_aligner=None,
+            frames_per_block=0,
+    ):
+        """EM for the cACGMM, signature of cacgmm.py:142-157.
+
+        Args:
+            y: (..., N, D) complex64/128; numpy array or CUDA tensor.
+            initialization: affiliations (..., K, N) (singleton independent
+                dims broadcast) or a ``CACGMM`` (warm start).
+            num_classes: K, if no initialization is given (the init is then
+                drawn from NumPy's global RNG exactly like cacgmm.py:206-209).
+            saliency: (..., N); source_activity_mask: bool (..., K, N).
+            weight_constant_axis: (-1,) or -2 on the device.
+            covariance_norm: 'eigenvalue', 'trace' or False.
+            frames_per_block: tuning knob of the EM kernel (0 = default).
+        Returns: CACGMM
+        """
+        assert xor(initialization is None, num_classes is None), (
+            'Incompatible input combination. '
+            'Exactly one of the two inputs has to be None: '
+            f'{initialization is None} xor {num_classes is None}')
+        if inline_permutation_aligner is not None:
+            raise NotImplementedError(
+                'inline_permutation_aligner couples the bins inside the EM '
+                'loop (SURVEY.md section 8f, rank 2); not on the device yet.')
+        assert covariance_norm in _NORMS, covariance_norm
+        like_numpy = not _device.is_tensor(y)
+        yd = _device.to_device(y)
+        assert yd.is_complex(), yd.dtype
+        assert yd.shape[-1] > 1, yd.shape
+        assert iterations > 0, iterations
+        code = _device.complex_dtype_code(yd)
+        independent, F, N, D = _flatten_obs(yd)
+        assert D < 35, f'Channels: {D}, sure?'
+
+        init_dev = None
+        model_in = None
+        if initialization is None:
+            K = num_classes
+            shape = (*independent, K, N)
+            aff = np.random.uniform(size=shape)
+            aff /= np.einsum('...kn->...n', aff)[..., None, :]
+            init_dev = _device.to_device(aff, torch.float64).reshape(F, K, N)
+        elif isinstance(initialization, CACGMM):
+            model_in = initialization
+            K = initialization.cacg.covariance_eigenvectors.shape[-3]
+        elif isinstance(initialization, (np.ndarray, torch.Tensor)):
+            K = initialization.shape[-2]
+            assert K > 1, K
+            shape = (*independent, K, N)
+            assert initialization.ndim == len(shape), (initialization.shape, shape)
+            assert tuple(initialization.shape[-2:]) == shape[-2:], (initialization.shape, shape)
+            init_dev = _device.to_device(initialization, torch.float64)
+            init_dev = init_dev.expand(shape).reshape(F, K, N).contiguous()
+        else:
+            raise TypeError('No sufficient initialization.')
+        assert K < 20, f'num_classes: {K}, sure?'
+        weight_mode = _weight_mode(weight_constant_axis, len(independent) + 2)
+
+        act = None
+        if source_activity_mask is not None:
+            assert source_activity_mask.dtype in (bool, np.bool_, torch.bool), source_activity_mask.dtype
+            assert tuple(source_activity_mask.shape[-2:]) == (K, N), (source_activity_mask.shape, K, N)
+            if isinstance(initialization, (np.ndarray, torch.Tensor)):
+                assert source_activity_mask.shape == initialization.shape, (
+                    source_activity_mask.shape, initialization.shape)
+            act = _device.to_device(source_activity_mask).to(torch.uint8)
+            act = act.expand(*independent, K, N).reshape(F, K, N).contiguous()
+        sal = None
+        if saliency is not None:
+            sal = _device.to_device(saliency, torch.float64)
+            sal = sal.expand(*independent, N).reshape(F, N).contiguous()
+
+        if model_in is not None:
+            V, lam, w, _ = model_in._device_model(independent, F)
+            V, lam, w = V.clone(), lam.clone(), w.clone()
+        else:
+            V = _device.empty((F, K, D, D), torch.complex128)
+            lam = _device.empty((F, K, D), torch.float64)
+            w = _device.empty((F, K), torch.float64)
+        status = _device.empty((1,), torch.int32)
+        opts = _lib.CacgmmOptions(
+            iterations=int(iterations), covariance_norm=_NORMS[covariance_norm],
+            weight_mode=weight_mode, hermitize=int(bool(hermitize)),
+            affiliation_eps=float(affiliation_eps),
+            eigenvalue_floor=float(eigenvalue_floor),
+            frames_per_block=int(frames_per_block), reserved=0)
+        lib = _lib.load()
+        nbytes = lib.pbb_cacgmm_workspace_bytes(F, N, D, K)
+        ws = _device.workspace(nbytes)
+        _lib.check(lib.pbb_cacgmm_fit(
+            _device.ptr(yd), code, F, N, D, K, _device.ptr(init_dev),
+            _device.ptr(sal), _device.ptr(act), ctypes.byref(opts),
+            _device.ptr(V), _device.ptr(lam), _device.ptr(w), _device.ptr(ws),
+            nbytes, _device.ptr(status), _device.stream_ptr()), 'pbb_cacgmm_fit')
+        _status_check(status, 'CACGMMTrainer.fit')
+
+        if weight_mode == _lib.WEIGHT_CONST:
+            weight = np.full([K, 1], 1 / K)  # mixture_model_utils.py:180-183
+            if not like_numpy:
+                weight = _device.to_device(weight)
+        else:
+            weight = _device.to_host(w.reshape(*independent, K, 1), like_numpy)
+        return CACGMM(
+            weight=weight,
+            cacg=ComplexAngularCentralGaussian(
+                covariance_eigenvectors=_device.to_host(
+                    V.reshape(*independent, K, D, D), like_numpy),
+                covariance_eigenvalues=_device.to_host(
+                    lam.reshape(*independent, K, D), like_numpy)))
+
+    def fit_predict(self, y, initialization=None, num_classes=None,
+                    iterations=100, **kwargs):
+        """Fit, then return the posterior affiliations (cacgmm.py:282-313)."""
+        model = self.fit(y=y, initialization=initialization,
+                         num_classes=num_classes, iterations=iterations,
+                         **kwargs)
+        return model.predict(y)
+
+    def _m_step(self, x, quadratic_form, affiliation, saliency, hermitize,
+                covariance_norm, eigenvalue_floor, weight_constant_axis):
+        """One M-step, signature of cacgmm.py:315-345; ``x`` is the normalised
+        observation in the reference's internal (..., D, N) layout."""
+        if _device.is_tensor(x):
+            y = x.transpose(-1, -2)
+        else:
+            y = np.swapaxes(x, -1, -2)
+        return cacgmm_m_step(
+            y, quadratic_form, affiliation, saliency=saliency,
+            hermitize=hermitize, covariance_norm=covariance_norm,
+            eigenvalue_floor=eigenvalue_floor,
+            weight_constant_axis=weight_constant_axis)
+
+
+def cacgmm_m_step(y, quadratic_form, affiliation, *, saliency=None,
+                  hermitize=True, covariance_norm='eigenvalue',
+                  eigenvalue_floor=1e-10, weight_constant_axis=(-1,)):
+    """One M-step from given affiliations / quadratic forms (``pbb_cacgmm_mstep``).
+
+    estimate_mixture_weight (mixture_model_utils.py:133-203) +
+    ComplexAngularCentralGaussianTrainer._fit (cacg.py:253-342).
+    y: (..., N, D); affiliation, quadratic_form: (..., K, N);
+    quadratic_form=None means ones (the first EM iteration, cacgmm.py:210).
+    """
+    like_numpy = not _device.is_tensor(y)
+    yd = _device.to_device(y)
+    code = _device.complex_dtype_code(yd)
+    independent, F, N, D = _flatten_obs(yd)
+    aff = _device.to_device(affiliation, torch.float64)
+    K = aff.shape[-2]
+    aff = aff.expand(*independent, K, N).reshape(F, K, N).contiguous()
+    q = None
+    if quadratic_form is not None:
+        q = _device.to_device(quadratic_form, torch.float64)
+        q = q.expand(*independent, K, N).reshape(F, K, N).contiguous()
+    sal = None
+    if saliency is not None:
+        sal = _device.to_device(saliency, torch.float64)
+        sal = sal.expand(*independent, N).reshape(F, N).contiguous()
+    weight_mode = _weight_mode(weight_constant_axis, len(independent) + 2)
+    V = _device.empty((F, K, D, D), torch.complex128)
+    lam = _device.empty((F, K, D), torch.float64)
+    w = _device.empty((F, K), torch.float64)
+    status = _device.empty((1,), torch.int32)
+    opts = _lib.CacgmmOptions(
+        iterations=1, covariance_norm=_NORMS[covariance_norm],
+        weight_mode=weight_mode, hermitize=int(bool(hermitize)),
+        affiliation_eps=0., eigenvalue_floor=float(eigenvalue_floor),
+        frames_per_block=0, reserved=0)
+    lib = _lib.load()
+    nbytes = lib.pbb_cacgmm_workspace_bytes(F, N, D, K)
+    ws = _device.workspace(nbytes)
+    _lib.check(lib.pbb_cacgmm_mstep(
+        _device.ptr(yd), code, F, N, D, K, _device.ptr(aff), _device.ptr(q),
+        _device.ptr(sal), ctypes.byref(opts), _device.ptr(V), _device.ptr(lam),
+        _device.ptr(w), _device.ptr(ws), nbytes, _device.ptr(status),
+        _device.stream_ptr()), 'pbb_cacgmm_mstep')
+    _status_check(status, 'cacgmm_m_step')
+    if weight_mode == _lib.WEIGHT_CONST:
+        weight = np.full([K, 1], 1 / K)
+        if not like_numpy:
+            weight = _device.to_device(weight)
+    else:
+        weight = _device.to_host(w.reshape(*independent, K, 1), like_numpy)
+    return CACGMM(
+        weight=weight,
+        cacg=ComplexAngularCentralGaussian(
+            covariance_eigenvectors=_device.to_host(
+                V.reshape(*independent, K, D, D), like_numpy),
+            covariance_eigenvalues=_device.to_host(
+                lam.reshape(*independent, K, D), like_numpy)))

@@ -1,0 +1,240 @@
+"""Parity of the CUDA cACGMM path (through the Python API -> C ABI) against
+the golden fixtures produced by the reference and against the oracle.
+
+Tolerances (fp64 everywhere; only the summation order differs from NumPy):
+single E/M steps rtol 1e-10; models after <= 10 EM iterations rtol 1e-6 /
+atol 1e-9 (near-singular covariances amplify rounding through 1/lambda)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pb_bss_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    'cacgmm_d4k2', 'cacgmm_d8k3', 'cacgmm_d8k3_structured',
+    'cacgmm_opt_saliency', 'cacgmm_opt_mask', 'cacgmm_opt_trace',
+    'cacgmm_opt_nonorm', 'cacgmm_opt_w2', 'cacgmm_opt_eps0',
+    'cacgmm_opt_bcast',
+]
+
+
+def _kwargs(g):
+    kw = {}
+    for k, v in g.items():
+        if not k.startswith('kw_'):
+            continue
+        name = k[3:]
+        if name == 'covariance_norm':
+            v = str(v) if v.dtype.kind in 'US' else False
+        elif name == 'weight_constant_axis':
+            v = int(v)
+        elif name in ('affiliation_eps', 'eigenvalue_floor'):
+            v = float(v)
+        kw[name] = v
+    return kw
+
+
+def _cov(model):
+    return model.cacg.covariance
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_fit_matches_reference_golden(name):
+    from pb_bss_b200.distribution import CACGMMTrainer
+    g = load_golden(name)
+    kw = _kwargs(g)
+    model = CACGMMTrainer().fit(g['y'], initialization=g['init'],
+                                iterations=int(g['iterations']), **kw)
+    assert model.weight.shape == g['weight'].shape
+    assert model.cacg.covariance_eigenvectors.shape == g['eigenvectors'].shape
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.cacg.covariance_eigenvalues, g['eigenvalues'], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(_cov(model), g['covariance'], rtol=1e-6, atol=1e-9)
+    aff, q = model.predict(g['y'], return_quadratic_form=True,
+                           source_activity_mask=kw.get('source_activity_mask'))
+    np.testing.assert_allclose(aff, g['affiliation'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(q, g['quadratic_form'], rtol=1e-6)
+    np.testing.assert_allclose(model.log_likelihood(g['y']), g['log_likelihood'], rtol=1e-8)
+    # eigenvectors: unitary, and they reproduce the covariance with the eigenvalues
+    V = model.cacg.covariance_eigenvectors
+    eye = np.eye(V.shape[-1])
+    np.testing.assert_allclose(np.einsum('...de,...df->...ef', V.conj(), V), np.broadcast_to(eye, V.shape), atol=1e-12)
+    assert np.all(np.diff(model.cacg.covariance_eigenvalues, axis=-1) >= 0)
+
+
+def test_warm_start_matches_reference():
+    from pb_bss_b200.distribution import CACGMM, CACGMMTrainer
+    from pb_bss_b200.distribution import ComplexAngularCentralGaussian as CACG
+    g = load_golden('cacgmm_warm')
+    m3 = CACGMM(weight=g['w3'], cacg=CACG(covariance_eigenvectors=g['V3'], covariance_eigenvalues=g['l3']))
+    m5 = CACGMMTrainer().fit(g['y'], initialization=m3, iterations=2)
+    np.testing.assert_allclose(m5.weight, g['w5'], rtol=1e-7)
+    np.testing.assert_allclose(m5.cacg.covariance_eigenvalues, g['l5'], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(_cov(m5), g['cov5'], rtol=1e-6, atol=1e-9)
+    # 3 + 2 iterations == 5 iterations in one go
+    m5b = CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=5)
+    np.testing.assert_allclose(_cov(m5b), g['cov5'], rtol=1e-6, atol=1e-9)
+
+
+def test_single_e_and_m_step():
+    from pb_bss_b200.distribution import CACGMM
+    from pb_bss_b200.distribution import ComplexAngularCentralGaussian as CACG
+    from pb_bss_b200.distribution.cacgmm import cacgmm_m_step
+    g = load_golden('cacg_steps')
+    model = CACGMM(weight=g['w'], cacg=CACG(covariance_eigenvectors=g['V'], covariance_eigenvalues=g['lam']))
+    aff, q = model.predict(g['y'], return_quadratic_form=True)
+    np.testing.assert_allclose(q, g['q'], rtol=1e-10)
+    aff_ref = O.log_pdf_to_affiliation(g['w'], g['log_pdf'], None, 0.)
+    np.testing.assert_allclose(aff, aff_ref, rtol=1e-9, atol=1e-300)
+    m2 = cacgmm_m_step(g['y'], g['q'], g['aff'])
+    np.testing.assert_allclose(m2.cacg.covariance_eigenvalues, g['fit_lam'], rtol=1e-9)
+    np.testing.assert_allclose(m2.cacg.covariance, g['fit_cov'], rtol=1e-9, atol=1e-12)
+
+
+def test_normalize_observation():
+    from pb_bss_b200.distribution import normalize_observation
+    y = synth.noise_stft(5, 77, 6, seed=3)
+    y[2, 5] = 0  # zero vectors stay zero (utils.py:242-244)
+    z = normalize_observation(y)
+    np.testing.assert_allclose(z, O.normalize_observation_cacg(y), rtol=1e-15)
+    assert np.all(z[2, :, 5] == 0)
+    z32 = normalize_observation(y.astype(np.complex64))
+    assert z32.dtype == np.complex64
+    np.testing.assert_allclose(z32, O.normalize_observation_cacg(y), rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('F,T,D,K,I', [
+    (129, 200, 4, 2, 20),   # BASELINE.json config 1
+    (7, 33, 8, 3, 5), (3, 31, 6, 4, 4), (2, 500, 8, 2, 6), (1, 7, 4, 3, 3),
+    (4, 64, 3, 2, 5), (3, 130, 5, 5, 4), (2, 40, 2, 2, 6), (2, 50, 9, 3, 3),  # generic kernel
+])
+def test_fit_matches_oracle(F, T, D, K, I):
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y, _ = synth.structured_stft(F, T, D, K, seed=F + T)
+    init = synth.init_affiliation(F, K, T, seed=D)
+    ref = O.cacgmm_fit(y, init, I)
+    model = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+    np.testing.assert_allclose(model.weight, ref['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), O.cacg_covariance_from_eig(ref['eigenvectors'], ref['eigenvalues']),
+                               rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.predict(y), O.cacgmm_predict(y, ref), rtol=1e-6, atol=1e-9)
+
+
+def test_leading_independent_dims_and_fit_predict():
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y, _ = synth.structured_stft(6, 48, 4, 2, seed=4)
+    init = synth.init_affiliation(6, 2, 48, seed=2)
+    y4, init4 = y.reshape(2, 3, 48, 4), init.reshape(2, 3, 2, 48)
+    m = CACGMMTrainer().fit(y4, initialization=init4, iterations=4)
+    assert m.weight.shape == (2, 3, 2, 1)
+    assert m.cacg.covariance_eigenvectors.shape == (2, 3, 2, 4, 4)
+    ref = O.cacgmm_fit(y, init, 4)
+    np.testing.assert_allclose(m.weight.reshape(6, 2, 1), ref['weight'], rtol=1e-7)
+    aff = CACGMMTrainer().fit_predict(y4, initialization=init4, iterations=4)
+    assert aff.shape == (2, 3, 2, 48)
+    np.testing.assert_allclose(aff.reshape(6, 2, 48), O.cacgmm_predict(y, ref), rtol=1e-6, atol=1e-9)
+
+
+def test_num_classes_uses_global_numpy_rng():
+    """fit(num_classes=K) draws its init like cacgmm.py:206-209."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y = synth.noise_stft(3, 40, 4, seed=1)
+    np.random.seed(5)
+    m = CACGMMTrainer().fit(y, num_classes=2, iterations=3)
+    np.random.seed(5)
+    init = np.random.uniform(size=(3, 2, 40))
+    init /= np.einsum('...kn->...n', init)[..., None, :]
+    ref = O.cacgmm_fit(y, init, 3)
+    np.testing.assert_allclose(m.weight, ref['weight'], rtol=1e-8)
+
+
+def test_complex64_storage():
+    """complex64 observations are stored as float2 and accumulated in fp64."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y, _ = synth.structured_stft(5, 120, 8, 3, seed=9)
+    init = synth.init_affiliation(5, 3, 120, seed=1)
+    y32 = y.astype(np.complex64)
+    ref = O.cacgmm_fit(y32.astype(np.complex128), init, 6)
+    m = CACGMMTrainer().fit(y32, initialization=init, iterations=6)
+    np.testing.assert_allclose(m.weight, ref['weight'], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(m.predict(y32), O.cacgmm_predict(y32.astype(np.complex128), ref), atol=1e-3)
+
+
+def test_device_tensors_stay_on_device_and_are_deterministic():
+    import torch
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y = torch.from_numpy(synth.noise_stft(9, 100, 8, seed=2)).cuda()
+    init = torch.from_numpy(synth.init_affiliation(9, 3, 100)).cuda()
+    m1 = CACGMMTrainer().fit(y, initialization=init, iterations=5)
+    m2 = CACGMMTrainer().fit(y, initialization=init, iterations=5)
+    assert m1.weight.is_cuda and m1.cacg.covariance_eigenvectors.is_cuda
+    assert torch.equal(m1.weight, m2.weight)
+    assert torch.equal(m1.cacg.covariance_eigenvalues, m2.cacg.covariance_eigenvalues)
+    aff = m1.predict(y)
+    assert aff.is_cuda and aff.shape == (9, 3, 100)
+    torch.testing.assert_close(aff.sum(-2), torch.ones_like(aff[:, 0]), rtol=0, atol=1e-12)
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 (F=513, T=500, D=8, K=3, 100 iterations):
+    size-independent properties instead of an oracle run."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    F, T, D, K = 513, 500, 8, 3
+    y = synth.noise_stft(F, T, D, seed=0)
+    init = synth.init_affiliation(F, K, T, seed=7)
+    tr = CACGMMTrainer()
+    m2 = tr.fit(y, initialization=init, iterations=2)
+    m3 = tr.fit(y, initialization=m2, iterations=1)
+    m100 = tr.fit(y, initialization=init, iterations=100)
+    ll2, ll3, ll100 = m2.log_likelihood(y), m3.log_likelihood(y), m100.log_likelihood(y)
+    assert ll3 > ll2 and ll100 > ll3, (ll2, ll3, ll100)  # cacgmm.py:100-107 doctest
+    np.testing.assert_allclose(m100.weight.sum(-2), 1, atol=1e-12)
+    lam = m100.cacg.covariance_eigenvalues
+    np.testing.assert_allclose(lam[..., -1], 1, rtol=1e-14)
+    assert np.all(lam >= 1e-10) and np.all(np.diff(lam, axis=-1) >= 0)
+    aff = m100.predict(y)
+    np.testing.assert_allclose(aff.sum(-2), 1, atol=1e-12)
+    # spot-check 3 bins of the 100-iteration model against the oracle
+    sel = [0, 256, 512]
+    ref = O.cacgmm_fit(y[sel], init[sel], 100)
+    np.testing.assert_allclose(m100.weight[sel], ref['weight'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(aff[sel], O.cacgmm_predict(y[sel], ref), atol=1e-5)
+
+
+def test_argument_errors():
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y = synth.noise_stft(2, 20, 4)
+    with pytest.raises(AssertionError):
+        CACGMMTrainer().fit(y)  # neither initialization nor num_classes
+    with pytest.raises(AssertionError):
+        CACGMMTrainer().fit(y.real, num_classes=2)
+    with pytest.raises(TypeError):
+        CACGMMTrainer().fit(y, initialization='nope')
+    with pytest.raises(AssertionError):
+        CACGMMTrainer().fit(y, num_classes=2, iterations=0)
+    with pytest.raises(NotImplementedError):
+        CACGMMTrainer().fit(y, num_classes=2, weight_constant_axis=(-3,))
+
+
+def test_nonfinite_input_raises():
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y = synth.noise_stft(3, 40, 4)
+    y[1, 3, 2] = np.nan
+    with pytest.raises(AssertionError):
+        CACGMMTrainer().fit(y, num_classes=2, iterations=2)
+
+
+def test_heig_batched():
+    from pb_bss_b200.extraction.linalg import eigh
+    for D in (2, 3, 6, 8, 13):
+        a = synth.pos_def_hermitian(50, D, D, seed=D)
+        a[3] = np.eye(D)          # degenerate spectrum
+        a[4] = np.diag(np.arange(D, 0, -1.0))  # needs sorting
+        w, v = eigh(a)
+        w0 = np.linalg.eigvalsh(a)
+        np.testing.assert_allclose(w, w0, rtol=1e-12, atol=1e-14)
+        rec = np.einsum('nde,ne,nfe->ndf', v, w, v.conj())
+        np.testing.assert_allclose(rec, a, rtol=1e-12, atol=1e-13)
