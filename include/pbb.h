@@ -50,6 +50,16 @@ extern "C" {
 const char* pbb_last_error(void);
 int pbb_version(void);
 
+/* Launch accounting and optional CUDA-event timing of the library's own kernels
+ * (used by bench.py for `gpu_launches` and the roofline of the dominant kernel). */
+long long pbb_launch_count(void);
+void pbb_profile_enable(int on);
+void pbb_profile_reset(void);
+/* Sums the recorded launches per kernel, returns the kernel with the largest
+ * total device time (ms) and its launch count, and clears the records.
+ * Synchronises on the recorded events.  Return value: number of distinct kernels. */
+int pbb_profile_dominant(char* name, int name_len, double* total_ms, int* launches);
+
 /* ------------------------------------------------------------------------
  * Observation normalisation.
  * swap=1: pb_bss/distribution/complex_angular_central_gaussian.py:34-55
@@ -78,7 +88,7 @@ typedef struct pbb_cacgmm_options {
   double affiliation_eps;  /* clip of the posterior, cacgmm.py:154 */
   double eigenvalue_floor; /* cacgmm.py:155 */
   int frames_per_block;    /* 0 = library default; tuning knob */
-  int reserved;
+  int reserved;            /* bit 0: force the multi-kernel (non-persistent) path */
 } pbb_cacgmm_options;
 
 /* Bytes of scratch pbb_cacgmm_fit / _predict need for this problem size. */

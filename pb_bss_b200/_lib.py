@@ -34,6 +34,10 @@ _vp, _i, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size
 SIGNATURES = {
     'pbb_last_error': (ctypes.c_char_p, []),
     'pbb_version': (_i, []),
+    'pbb_launch_count': (ctypes.c_longlong, []),
+    'pbb_profile_enable': (None, [_i]),
+    'pbb_profile_reset': (None, []),
+    'pbb_profile_dominant': (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_d), ctypes.POINTER(_i)]),
     'pbb_normalize_observation': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'pbb_cacgmm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'pbb_cacgmm_fit': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,

@@ -3,6 +3,8 @@
 #include <cstring>
 
 #include "em_kernels.cuh"
+#include "em_persistent.cuh"
+#include "prof.cuh"
 
 namespace pbb {
 
@@ -34,6 +36,9 @@ __global__ void sum_rows_kernel(const double* in, double* out, int rows, int n) 
 // ---- workspace carving -------------------------------------------------------
 struct CacgmmWorkspace {
   void* z;
+  int zs;       // padded row stride of z (frames)
+  int* flags;   // (F) per-bin model version, persistent kernel
+  int* ticket;  // (1)
   double* part;
   double* coef;
   double* ld;
@@ -50,7 +55,9 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t NS = (size_t)D * D;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return o; };
-  const size_t o_z = take((size_t)F * D * T * sizeof(double2));
+  const int zs = (T + 31) / 32 * 32;
+  const size_t o_z = take((size_t)F * D * zs * sizeof(double2));
+  const size_t o_flags = take((size_t)(F + 1) * sizeof(int));
   const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
   const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
   const size_t o_ld = take((size_t)F * K * sizeof(double));
@@ -59,6 +66,9 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t o_ll = take((size_t)F * max_chunks(T) * sizeof(double));
   char* b = reinterpret_cast<char*>(base);
   ws.z = b + o_z;
+  ws.zs = zs;
+  ws.flags = reinterpret_cast<int*>(b + o_flags);
+  ws.ticket = ws.flags + F;
   ws.part = reinterpret_cast<double*>(b + o_part);
   ws.coef = reinterpret_cast<double*>(b + o_coef);
   ws.ld = reinterpret_cast<double*>(b + o_ld);
@@ -71,12 +81,13 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
 
 // ---- launches ------------------------------------------------------------------
 template <typename CT>
-static int launch_normalize(const void* y, void* z, int F, int T, int D, int swap, cudaStream_t st) {
+static int launch_normalize(const void* y, void* z, int F, int T, int D, int swap, int zs, cudaStream_t st) {
   const int block = D <= 16 ? 128 : 32;
   dim3 grid((T + block - 1) / block, F);
   const size_t smem = (size_t)block * (D + 1) * sizeof(double2);
+  LaunchScope ls("normalize_kernel", st);
   normalize_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T,
-                                                    D, swap);
+                                                    D, swap, zs);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -86,6 +97,7 @@ static bool fast_shape(int D, int K) { return (D == 4 || D == 6 || D == 8) && K 
 template <int D, int K>
 static cudaError_t launch_fast_dk(const EmArgs& a, int dtype, cudaStream_t st) {
   dim3 grid(a.nch, a.F);
+  LaunchScope ls("em_fast_kernel", st);
   if (dtype == PBB_C128) em_fast_kernel<D, K, double2><<<grid, 32 * kEmGroups, 0, st>>>(a);
   else em_fast_kernel<D, K, float2><<<grid, 32 * kEmGroups, 0, st>>>(a);
   return cudaGetLastError();
@@ -122,6 +134,7 @@ static int launch_em(EmArgs a, int dtype, int frames_per_block, cudaStream_t st)
   a.softmax_fast = 0;
   dim3 grid(a.nch, a.F);
   const size_t smem = (size_t)2 * a.K * kGenFrames * sizeof(double) + (size_t)a.D * a.D * sizeof(int);
+  LaunchScope ls("em_generic_kernel", st);
   if (dtype == PBB_C128) {
     PBB_CUDA(cudaFuncSetAttribute(em_generic_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     em_generic_kernel<double2><<<grid, kGenFrames, smem, st>>>(a);
@@ -148,6 +161,7 @@ static int launch_update(UpdArgs u, cudaStream_t st) {
                       (size_t)u.D * u.D * sizeof(int);
   PBB_CUDA(cudaFuncSetAttribute(cacg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const int threads = 32 * u.warps < u.K ? ((u.K + 31) / 32 * 32) : 32 * u.warps;
+  LaunchScope ls("cacg_update_kernel", st);
   cacg_update_kernel<<<u.F, threads, smem, st>>>(u);
   PBB_CUDA(cudaGetLastError());
   return 0;
@@ -162,9 +176,59 @@ static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
   const size_t smem = per * w + (size_t)u.K * sizeof(double) + (size_t)u.D * u.D * sizeof(int);
   PBB_CUDA(cudaFuncSetAttribute(cacg_from_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const int threads = 32 * w < u.K ? ((u.K + 31) / 32 * 32) : 32 * w;
+  LaunchScope ls("cacg_from_eig_kernel", st);
   cacg_from_eig_kernel<<<u.F, threads, smem, st>>>(u);
   PBB_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---- persistent kernel launch ---------------------------------------------------
+template <int D, int K, typename CT, bool FULL>
+static int launch_persist_t(const PersistArgs& a, cudaStream_t st) {
+  auto kern = em_persistent_kernel<D, K, CT, FULL>;
+  const size_t smem = sizeof(PersistSmem<D, K, CT>);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    PBB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 32 * (D / 2), smem));
+    if (n < 1) { set_error("persistent EM kernel does not fit on this device"); return 1; }
+    ctas_per_sm = n;
+  }
+  int dev = 0, sms = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long grid = (long long)ctas_per_sm * sms;
+  const long long tasks = (long long)a.iterations * a.F;
+  if (grid > tasks) grid = tasks;
+  LaunchScope ls("em_persistent_kernel", st);
+  kern<<<(unsigned)grid, 32 * (D / 2), smem, st>>>(a);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int D, int K>
+static int launch_persist_dk(const PersistArgs& a, int dtype, bool full, cudaStream_t st) {
+  if (dtype == PBB_C128)
+    return full ? launch_persist_t<D, K, double2, true>(a, st) : launch_persist_t<D, K, double2, false>(a, st);
+  return full ? launch_persist_t<D, K, float2, true>(a, st) : launch_persist_t<D, K, float2, false>(a, st);
+}
+
+template <int D>
+static int launch_persist_d(const PersistArgs& a, int K, int dtype, bool full, cudaStream_t st) {
+  switch (K) {
+    case 2: return launch_persist_dk<D, 2>(a, dtype, full, st);
+    case 3: return launch_persist_dk<D, 3>(a, dtype, full, st);
+    default: return launch_persist_dk<D, 4>(a, dtype, full, st);
+  }
+}
+
+static int launch_persist(const PersistArgs& a, int D, int K, int dtype, bool full, cudaStream_t st) {
+  switch (D) {
+    case 4: return launch_persist_d<4>(a, K, dtype, full, st);
+    case 6: return launch_persist_d<6>(a, K, dtype, full, st);
+    default: return launch_persist_d<8>(a, K, dtype, full, st);
+  }
 }
 
 static bool softmax_fast_ok(int D, const pbb_cacgmm_options* o) {
@@ -198,8 +262,8 @@ int pbb_normalize_observation(const void* y, void* z, int F, int T, int D, int d
   PBB_CHECK_ARG(D > 0 && D < 256, 5, "bad D");
   PBB_CHECK_ARG(dtype == PBB_C64 || dtype == PBB_C128, 6, "bad dtype");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return dtype == PBB_C128 ? launch_normalize<double2>(y, z, F, T, D, swap, st)
-                           : launch_normalize<float2>(y, z, F, T, D, swap, st);
+  return dtype == PBB_C128 ? launch_normalize<double2>(y, z, F, T, D, swap, T, st)
+                           : launch_normalize<float2>(y, z, F, T, D, swap, T, st);
 }
 
 size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K) {
@@ -224,13 +288,13 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
-                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
   if (r) return r;
 
   EmArgs a;
   memset(&a, 0, sizeof(a));
-  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
   a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
   a.activity = activity; a.aff_eps = opt->affiliation_eps;
   a.saliency = saliency; a.part = ws.part;
@@ -249,6 +313,34 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   u.status = status;
 
   const bool fast_sm = softmax_fast_ok(D, opt);
+  if (fast_shape(D, K) && !(opt->reserved & 1)) {
+    // ---- persistent path: every EM iteration in one launch (em_persistent.cuh) ----
+    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int), st));
+    if (init_aff == nullptr) {
+      FromEigArgs fe;
+      fe.F = F; fe.D = D; fe.K = K;
+      fe.evec = reinterpret_cast<const double2*>(eigenvectors);
+      fe.eval = eigenvalues; fe.weight = weight;
+      fe.coef = ws.coef; fe.ld = ws.ld; fe.w = ws.w; fe.ew = ws.ew;
+      if ((r = launch_from_eig(fe, st))) return r;
+    }
+    PersistArgs p;
+    memset(&p, 0, sizeof(p));
+    p.z = ws.z; p.zs = ws.zs; p.F = F; p.T = T;
+    p.iterations = opt->iterations;
+    p.first_is_m = init_aff != nullptr;
+    p.user_model = init_aff == nullptr;
+    p.softmax_fast = fast_sm;
+    p.aff_in = init_aff; p.saliency = saliency; p.activity = activity;
+    p.aff_eps = opt->affiliation_eps; p.eigenvalue_floor = opt->eigenvalue_floor;
+    p.covariance_norm = opt->covariance_norm; p.weight_mode = opt->weight_mode;
+    p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
+    p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
+    const bool full = saliency != nullptr || activity != nullptr || !fast_sm || p.user_model;
+    if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
+    u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model
+    return launch_update(u, st);
+  }
   int it = 0;
   if (init_aff != nullptr) {
     // iteration 0: M-step from the initial affiliations, q = 1 (cacgmm.py:206-228,269)
@@ -297,8 +389,8 @@ int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K, con
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
-                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
   if (r) return r;
   FromEigArgs fe;
   fe.F = F; fe.D = D; fe.K = K;
@@ -309,7 +401,7 @@ int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K, con
   if ((r = launch_from_eig(fe, st))) return r;
   EmArgs a;
   memset(&a, 0, sizeof(a));
-  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
   a.mode = kModeE; a.softmax_fast = 0;
   a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
   a.activity = activity; a.aff_eps = affiliation_eps;
@@ -340,12 +432,12 @@ int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, st)
-                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, st);
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
   if (r) return r;
   EmArgs a;
   memset(&a, 0, sizeof(a));
-  a.z = ws.z; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
   a.mode = kModeM; a.aff_in = affiliation; a.q_in = quadratic;
   a.saliency = saliency; a.part = ws.part;
   int nch = launch_em(a, dtype, opt->frames_per_block, st);

@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 OUT=../libpbb.so
 mkdir -p build
 pids=()
-for src in api_cacgmm api_linalg; do
+for src in api_cacgmm api_linalg prof; do
   if [ ! -f build/$src.o ] || [ $src.cu -nt build/$src.o ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer build/$src.o)" ] || [ ../../include/pbb.h -nt build/$src.o ]; then
     ( $NVCC $FLAGS -c $src.cu -o build/$src.o > build/$src.log 2>&1 || { cat build/$src.log; exit 1; } ) &
     pids+=($!)

@@ -43,37 +43,74 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 // ---- slot table -------------------------------------------------------------
 // A Hermitian D x D outer product z z^H has D*D real degrees of freedom
-// ("slots"): D real diagonals and D(D-1)/2 complex upper-triangle entries.
-// psi(d,e) = conj(z_d) * z_e.  Slot order: triangle over the first half of
-// the channels, triangle over the second half, then the first-half x
-// second-half rectangle row by row -- for D in {4, 8} four equal ranges of
-// this order are exactly the 2x2 block partition of the matrix, so a group of
-// slots touches only half (or three quarters) of the channels.
+// ("slots"): D real diagonals and D(D-1)/2 complex off-diagonal entries.  A slot
+// is (d, e, kind) with psi(d,e) = conj(z_d) * z_e (d may be larger than e: the
+// scatter matrix entry [d][e] is conj(psi), entry [e][d] is psi, and the
+// quadratic form picks up 2 Re(Binv[d][e] psi) either way).
+//
+// Even D: the channels form M = D/2 pairs P_0..P_{M-1}.  The slots are split
+// into M groups with IDENTICAL local structure, so M warps can run the same
+// instruction stream on different channels:
+//   group g owns pair P_g = (a0, a1):          |a0|^2, |a1|^2, (a0,a1)
+//   full cross with P_{g+1+j}, j < (M-1)/2:    (a0,b0) (a0,b1) (a1,b0) (a1,b1)
+//   if M is even, half cross with P_{g+M/2}:   (a0,c0) (a1,c1), where the lower
+//   half of the groups takes c in order and the upper half takes it swapped,
+//   which tiles the 2x2 cross block of the two pairs exactly once.
+// D=8: 4 groups x 16 slots (6 channels each); D=6: 3 x 12; D=4: 2 x 8.
+// Odd D: plain upper-triangle order (only the generic kernels use it).
 struct SlotInfo { int d, e, kind; };  // kind: 0 = diagonal, 1 = real part, 2 = imaginary part
 
-__host__ __device__ constexpr SlotInfo slot_info(int D, int s) {
-  const int H = D / 2;
-  int idx = 0;
-  for (int half = 0; half < 2; ++half) {
-    const int lo = half == 0 ? 0 : H, hi = half == 0 ? H : D;
-    for (int d = lo; d < hi; ++d) {
-      if (idx == s) return {d, d, 0};
-      ++idx;
-      for (int e = d + 1; e < hi; ++e) {
-        if (idx == s) return {d, e, 1};
-        ++idx;
-        if (idx == s) return {d, e, 2};
-        ++idx;
-      }
-    }
+struct GroupShape {
+  int M, nfull, half, nloc, nsg;
+};
+__host__ __device__ constexpr GroupShape group_shape(int D) {
+  const int M = D / 2;
+  const int nfull = (M - 1) / 2;
+  const int half = (M % 2 == 0) ? 1 : 0;
+  return {M, nfull, half, 2 + 2 * nfull + 2 * half, 4 + 8 * nfull + 4 * half};
+}
+// channel of local index l (0,1 = own pair; 2+2j, 3+2j = full cross j; last two = half cross)
+__host__ __device__ constexpr int group_channel(int D, int g, int l) {
+  const GroupShape gs = group_shape(D);
+  if (l < 2) return 2 * g + l;
+  const int j = (l - 2) / 2, r = (l - 2) % 2;
+  if (j < gs.nfull) return 2 * ((g + 1 + j) % gs.M) + r;
+  const int p = (g + gs.M / 2) % gs.M;
+  return g < gs.M / 2 ? 2 * p + r : 2 * p + (1 - r);
+}
+// local slot i of a group -> (local x, local y, kind)
+__host__ __device__ constexpr SlotInfo group_local_slot(int D, int i) {
+  const GroupShape gs = group_shape(D);
+  if (i == 0) return {0, 0, 0};
+  if (i == 1) return {1, 1, 0};
+  if (i < 4) return {0, 1, i - 1};
+  const int r = i - 4;
+  if (r < 8 * gs.nfull) {
+    const int j = r / 8, q = (r % 8) / 2, kind = 1 + (r % 2);
+    return {q / 2, 2 + 2 * j + (q % 2), kind};
   }
-  for (int d = 0; d < H; ++d)
-    for (int e = H; e < D; ++e) {
+  const int h = r - 8 * gs.nfull;  // 0..3
+  return {h / 2, 2 + 2 * gs.nfull + h / 2, 1 + (h % 2)};
+}
+
+__host__ __device__ constexpr SlotInfo slot_info(int D, int s) {
+  if (D % 2 == 0) {
+    const GroupShape gs = group_shape(D);
+    const int g = s / gs.nsg, i = s % gs.nsg;
+    const SlotInfo l = group_local_slot(D, i);
+    return {group_channel(D, g, l.d), group_channel(D, g, l.e), l.kind};
+  }
+  int idx = 0;
+  for (int d = 0; d < D; ++d) {
+    if (idx == s) return {d, d, 0};
+    ++idx;
+    for (int e = d + 1; e < D; ++e) {
       if (idx == s) return {d, e, 1};
       ++idx;
       if (idx == s) return {d, e, 2};
       ++idx;
     }
+  }
   return {-1, -1, -1};
 }
 

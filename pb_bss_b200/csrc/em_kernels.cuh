@@ -20,7 +20,8 @@ namespace pbb {
 enum EmMode { kModeM = 0, kModeEM = 1, kModeE = 2 };
 
 struct EmArgs {
-  const void* z;
+  const void* z;   // (F, D, zs): rows zero padded to zs frames
+  int zs;
   int F, T, D, K;
   int mode;          // EmMode
   int softmax_fast;  // integer-power softmax is safe (see em_softmax)
@@ -138,7 +139,8 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
   constexpr int NS = S::NS, NSG = S::NSG;
   constexpr unsigned need = slot_range_channels(D, GI * NSG, GI * NSG + NSG);
   const int T = a.T;
-  const CT* __restrict__ zf = reinterpret_cast<const CT*>(a.z) + (size_t)f * D * T;
+  const int zs = a.zs;
+  const CT* __restrict__ zf = reinterpret_cast<const CT*>(a.z) + (size_t)f * D * zs;
   const int t_begin = chunk * a.frames_per_block;
   const int t_end = min(T, t_begin + a.frames_per_block);
   const int mode = a.mode;
@@ -162,7 +164,7 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
       constexpr int d = decltype(dd)::value;
       if constexpr ((need >> d) & 1u) {
         double2 v = make_double2(0.0, 0.0);
-        if (valid) v = ld_cplx(zf + (size_t)d * T + t);
+        if (valid) v = ld_cplx(zf + (size_t)d * zs + t);
         zr[d] = v.x; zi[d] = v.y;
       }
     });
@@ -318,7 +320,8 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
   const int t_end = min(T, t_begin + kGenFrames);
   const int t = t_begin + tid;
   const bool valid = t < t_end;
-  const CT* __restrict__ zf = reinterpret_cast<const CT*>(a.z) + (size_t)f * D * T;
+  const int zs = a.zs;
+  const CT* __restrict__ zf = reinterpret_cast<const CT*>(a.z) + (size_t)f * D * zs;
   for (int s = tid; s < NS; s += blockDim.x) tab[s] = slot_pack(D, s);
   __syncthreads();
 
@@ -332,8 +335,8 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
       for (int s = 0; s < NS; ++s) {
         const int pk = tab[s];
         const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
-        const double2 zd = ld_cplx(zf + (size_t)d * T + t);
-        const double2 ze = ld_cplx(zf + (size_t)e * T + t);
+        const double2 zd = ld_cplx(zf + (size_t)d * zs + t);
+        const double2 ze = ld_cplx(zf + (size_t)e * zs + t);
         const double psi = kind == 2 ? zd.x * ze.y - zd.y * ze.x : zd.x * ze.x + zd.y * ze.y;
         for (int k = 0; k < K; ++k) q[k] = fma(cf[(size_t)k * NS + s], psi, q[k]);
       }
@@ -401,8 +404,8 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
     } else {
       const int pk = tab[s];
       const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
-      const CT* zd = zf + (size_t)d * T + t_begin;
-      const CT* ze = zf + (size_t)e * T + t_begin;
+      const CT* zd = zf + (size_t)d * zs + t_begin;
+      const CT* ze = zf + (size_t)e * zs + t_begin;
       for (int i = 0; i < nt; ++i) {
         const double2 vd = ld_cplx(zd + i), ve = ld_cplx(ze + i);
         const double psi = kind == 2 ? vd.x * ve.y - vd.y * ve.x : vd.x * ve.x + vd.y * ve.y;
@@ -622,7 +625,8 @@ __global__ void cacg_from_eig_kernel(const FromEigArgs u) {
 // both the read and the write are coalesced.
 // --------------------------------------------------------------------------
 template <typename CT>
-__global__ void normalize_kernel(const CT* __restrict__ y, CT* __restrict__ z, int F, int T, int D, int swap) {
+__global__ void normalize_kernel(const CT* __restrict__ y, CT* __restrict__ z, int F, int T, int D, int swap,
+                                 int zs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);  // [blockDim.x][D + 1]
   const int f = blockIdx.y;
@@ -658,7 +662,14 @@ __global__ void normalize_kernel(const CT* __restrict__ y, CT* __restrict__ z, i
     for (int i = threadIdx.x; i < nt * D; i += blockDim.x) {
       const int d = i / nt, tt = i - d * nt;
       const double2 v = tile[tt * ldt + d];
-      st_cplx(z + ((size_t)f * D + d) * T + t0 + tt, v.x, v.y);
+      st_cplx(z + ((size_t)f * D + d) * zs + t0 + tt, v.x, v.y);
+    }
+    if (t0 + (int)blockDim.x >= T) {  // zero the padding [T, zs) of every row
+      const int npad = zs - T;
+      for (int i = threadIdx.x; i < npad * D; i += blockDim.x) {
+        const int d = i / npad, tt = i - d * npad;
+        st_cplx(z + ((size_t)f * D + d) * zs + T + tt, 0.0, 0.0);
+      }
     }
   } else {
     CT* __restrict__ zf = z + ((size_t)f * T + t0) * D;

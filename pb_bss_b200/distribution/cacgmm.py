@@ -146,6 +146,7 @@ class CACGMMTrainer:
             eigenvalue_floor=1e-10,
             inline_permutation_aligner=None,
             frames_per_block=0,
+            multi_kernel=False,
     ):
         """EM for the cACGMM, signature of cacgmm.py:142-157.
 
@@ -158,7 +159,9 @@ class CACGMMTrainer:
             saliency: (..., N); source_activity_mask: bool (..., K, N).
             weight_constant_axis: (-1,) or -2 on the device.
             covariance_norm: 'eigenvalue', 'trace' or False.
-            frames_per_block: tuning knob of the EM kernel (0 = default).
+            frames_per_block: tuning knob of the multi-kernel EM path (0 = default).
+            multi_kernel: force the one-kernel-pair-per-iteration path instead
+                of the persistent kernel (A/B testing; same results).
         Returns: CACGMM
         """
         assert xor(initialization is None, num_classes is None), (
@@ -230,7 +233,8 @@ class CACGMMTrainer:
             weight_mode=weight_mode, hermitize=int(bool(hermitize)),
             affiliation_eps=float(affiliation_eps),
             eigenvalue_floor=float(eigenvalue_floor),
-            frames_per_block=int(frames_per_block), reserved=0)
+            frames_per_block=int(frames_per_block),
+            reserved=1 if multi_kernel else 0)
         lib = _lib.load()
         nbytes = lib.pbb_cacgmm_workspace_bytes(F, N, D, K)
         ws = _device.workspace(nbytes)

@@ -204,6 +204,36 @@ def test_full_size_properties():
     np.testing.assert_allclose(aff[sel], O.cacgmm_predict(y[sel], ref), atol=1e-5)
 
 
+@pytest.mark.parametrize('D,K', [(8, 3), (6, 4), (4, 2)])
+def test_persistent_and_multi_kernel_paths_agree(D, K):
+    """The persistent kernel (Gauss-Jordan update on intermediate iterations)
+    and the kernel-pair-per-iteration path (Jacobi every iteration) must agree."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y, _ = synth.structured_stft(40, 300, D, K, seed=3)
+    init = synth.init_affiliation(40, K, 300, seed=5)
+    a = CACGMMTrainer().fit(y, initialization=init, iterations=15)
+    b = CACGMMTrainer().fit(y, initialization=init, iterations=15, multi_kernel=True)
+    np.testing.assert_allclose(a.weight, b.weight, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(_cov(a), _cov(b), rtol=1e-7, atol=1e-10)
+
+
+def test_rank_deficient_observation_takes_the_floor_path():
+    """Observations confined to a 2-dim subspace: the scatter matrices are
+    singular, every update must take the eigendecomposition + floor path."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    rng = np.random.RandomState(0)
+    F, T, D, K = 6, 96, 8, 2
+    basis = rng.randn(F, 2, D) + 1j * rng.randn(F, 2, D)
+    coeff = rng.randn(F, T, 2) + 1j * rng.randn(F, T, 2)
+    y = np.einsum('ftr,frd->ftd', coeff, basis)
+    init = synth.init_affiliation(F, K, T, seed=2)
+    ref = O.cacgmm_fit(y, init, 4)
+    m = CACGMMTrainer().fit(y, initialization=init, iterations=4)
+    np.testing.assert_allclose(m.cacg.covariance_eigenvalues[..., :6], 1e-10, rtol=1e-6)
+    np.testing.assert_allclose(m.weight, ref['weight'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(m.predict(y), O.cacgmm_predict(y, ref), atol=1e-4)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
