@@ -185,7 +185,8 @@ static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
 // ---- persistent kernel launch ---------------------------------------------------
 template <int D, int K, typename CT, bool FULL>
 static int launch_persist_t(const PersistArgs& a, cudaStream_t st) {
-  auto kern = em_persistent_kernel<D, K, CT, FULL>;
+  // lean variant: two frames per lane and step (255 registers, 2 CTAs/SM)
+  auto kern = em_persistent_kernel<D, K, CT, FULL, FULL ? 1 : 2>;
   const size_t smem = sizeof(PersistSmem<D, K, CT>);
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
@@ -336,7 +337,9 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     p.covariance_norm = opt->covariance_norm; p.weight_mode = opt->weight_mode;
     p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
-    const bool full = saliency != nullptr || activity != nullptr || !fast_sm || p.user_model;
+    // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
+    const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
+    const bool full = saliency != nullptr || activity != nullptr || !lean_ok || p.user_model;
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
     u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model
     return launch_update(u, st);

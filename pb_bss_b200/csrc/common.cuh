@@ -69,15 +69,22 @@ __host__ __device__ constexpr GroupShape group_shape(int D) {
   const int half = (M % 2 == 0) ? 1 : 0;
   return {M, nfull, half, 2 + 2 * nfull + 2 * half, 4 + 8 * nfull + 4 * half};
 }
-// channel of local index l (0,1 = own pair; 2+2j, 3+2j = full cross j; last two = half cross)
-__host__ __device__ constexpr int group_channel(int D, int g, int l) {
+// Row layout of the staged observation: rows 0..D-1 are the channels; the rows
+// after that repeat the first channels (pair-swapped when M is even) so that
+// group g finds its NLOC local channels in the CONSECUTIVE rows 2g .. 2g+NLOC-1
+// -- one base address plus compile-time offsets for every group.
+//   D=8: rows = 0 1 2 3 4 5 6 7 | 1 0 3 2      D=6: 0..5 | 0 1      D=4: 0..3 | 1 0
+__host__ __device__ constexpr int stage_rows(int D) {
   const GroupShape gs = group_shape(D);
-  if (l < 2) return 2 * g + l;
-  const int j = (l - 2) / 2, r = (l - 2) % 2;
-  if (j < gs.nfull) return 2 * ((g + 1 + j) % gs.M) + r;
-  const int p = (g + gs.M / 2) % gs.M;
-  return g < gs.M / 2 ? 2 * p + r : 2 * p + (1 - r);
+  return 2 * (gs.M - 1) + gs.nloc;
 }
+__host__ __device__ constexpr int row_channel(int D, int r) {
+  if (r < D) return r;
+  const int x = r - D;
+  return (D / 2) % 2 == 0 ? (x ^ 1) : x;
+}
+// channel of local index l of group g (0,1 = own pair; then the full crosses; last two = half cross)
+__host__ __device__ constexpr int group_channel(int D, int g, int l) { return row_channel(D, 2 * g + l); }
 // local slot i of a group -> (local x, local y, kind)
 __host__ __device__ constexpr SlotInfo group_local_slot(int D, int i) {
   const GroupShape gs = group_shape(D);

@@ -124,11 +124,12 @@ template <int D, int K, typename CT>
 struct PersistSmem {
   static constexpr int NS = D * D;
   static constexpr int M = D / 2;
-  CT zbuf[kStages][D][kStageFrames];
+  static constexpr int ROWS = stage_rows(D);  // channels + repeated rows, see common.cuh
+  CT zbuf[kStages][ROWS][kStageFrames];
   double2 A[K][NS];     // scatter matrix / its inverse
   double2 V[K][NS];     // eigenvectors (Jacobi fallback only)
   double coef[K][NS];   // E-step form of the bin's model
-  double xq[2][M][K][32];
+  double xq[2][M][2 * K][32];  // partial quadratic forms, up to 2 frames per lane
   double S[K][NS + 1];  // scatter sums + sum of gamma
   double rot[K][((D + 1) / 2) * 6];
   double lam[K][D];
@@ -138,40 +139,222 @@ struct PersistSmem {
   int tick[2];
 };
 
-// One EM step of 32 frames for slot group g.  FULL adds saliency / activity /
-// the log-domain softmax.
-template <int D, int K, typename CT, bool FULL>
-struct PersistStep {
+template <int D>
+struct GroupDims {
   static constexpr int NSG = group_shape(D).nsg, NLOC = group_shape(D).nloc, NS = D * D;
-  static constexpr int NFULL = group_shape(D).nfull, HALF = group_shape(D).half;
+  static constexpr int NFULL = group_shape(D).nfull, HALF = group_shape(D).half, M = D / 2;
+};
 
-  __device__ static __forceinline__ void psi_of(const double2 (&x)[NLOC], double (&psi)[NSG]) {
-    psi[0] = x[0].x * x[0].x + x[0].y * x[0].y;
-    psi[1] = x[1].x * x[1].x + x[1].y * x[1].y;
-    psi[2] = x[0].x * x[1].x + x[0].y * x[1].y;
-    psi[3] = x[0].x * x[1].y - x[0].y * x[1].x;
+// psi slots of one group from its NLOC local channels (order: group_local_slot)
+template <int D>
+__device__ __forceinline__ void group_psi(const double2 (&x)[GroupDims<D>::NLOC], double (&psi)[GroupDims<D>::NSG]) {
+  using G = GroupDims<D>;
+  psi[0] = x[0].x * x[0].x + x[0].y * x[0].y;
+  psi[1] = x[1].x * x[1].x + x[1].y * x[1].y;
+  psi[2] = x[0].x * x[1].x + x[0].y * x[1].y;
+  psi[3] = x[0].x * x[1].y - x[0].y * x[1].x;
 #pragma unroll
-    for (int j = 0; j < NFULL; ++j) {
+  for (int j = 0; j < G::NFULL; ++j) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double2 u = x[q / 2], v = x[2 + 2 * j + (q % 2)];
-        psi[4 + 8 * j + 2 * q] = u.x * v.x + u.y * v.y;
-        psi[4 + 8 * j + 2 * q + 1] = u.x * v.y - u.y * v.x;
+    for (int q = 0; q < 4; ++q) {
+      const double2 u = x[q / 2], v = x[2 + 2 * j + (q % 2)];
+      psi[4 + 8 * j + 2 * q] = u.x * v.x + u.y * v.y;
+      psi[4 + 8 * j + 2 * q + 1] = u.x * v.y - u.y * v.x;
+    }
+  }
+  if (G::HALF) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double2 u = x[h], v = x[2 + 2 * G::NFULL + h];
+      psi[4 + 8 * G::NFULL + 2 * h] = u.x * v.x + u.y * v.y;
+      psi[4 + 8 * G::NFULL + 2 * h + 1] = u.x * v.y - u.y * v.x;
+    }
+  }
+}
+
+// ---- posterior of one frame, product form -------------------------------------
+// gamma_k ~ ew_k / q_k^D  =  ew_k * (prod_{j != k} q_j)^D / (prod_j q_j)^D : no
+// logarithm, exponential, minimum or per-class division.  The host enables it
+// only when (K-1) * D * log10(1/floor) < 290 so the products stay in range;
+// q_k lies in [1/D, 1/floor] after the update's trace normalisation.  A frame
+// whose observation is the zero vector has every q_k = 0; the reference floors
+// those at `tiny` (cacg.py:198), which makes all classes equal -- reproduced by
+// mapping such a frame to q_k = 1.
+// Outputs gamma_k (clipped, mixture_model_utils.py:50-53) and
+// cw_k = gamma_k / q_k (cacg.py:316-325).
+template <int D, int K>
+__device__ __forceinline__ void softmax_product(double (&q)[K], const double* __restrict__ ew, double eps,
+                                                double (&gam)[K], double (&cw)[K]) {
+  const bool dead = q[0] < 1e-200;
+#pragma unroll
+  for (int k = 0; k < K; ++k) q[k] = dead ? 1.0 : q[k];
+  double P[K];
+  if constexpr (K == 2) {
+    P[0] = q[1]; P[1] = q[0];
+  } else if constexpr (K == 3) {
+    P[0] = q[1] * q[2]; P[1] = q[0] * q[2]; P[2] = q[0] * q[1];
+  } else {
+    const double q01 = q[0] * q[1], q23 = q[2] * q[3];
+    P[0] = q[1] * q23; P[1] = q[0] * q23; P[2] = q01 * q[3]; P[3] = q01 * q[2];
+  }
+  double b[K];
+  double S = 1e-300;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    b[k] = ew[k] * ipow<D>(P[k]);
+    S += b[k];
+  }
+  const double rS = fast_rcp(S);
+  const double rQ = fast_rcp(q[0] * P[0]);
+  const double hi = 1.0 - eps;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double g = b[k] * rS;
+    if (eps != 0.0) {
+      g = g < eps ? eps : g;
+      g = g > hi ? hi : g;
+    }
+    gam[k] = g;
+    cw[k] = g * (P[k] * rQ);
+  }
+}
+
+// Hot loop of the lean variant: E-step + M-step of one ring stage for slot
+// group g.  All warps run the same instructions (one loop body in the L0
+// instruction cache); the staged rows are laid out so that the group's local
+// channels are rows 2g .. 2g+NLOC-1, i.e. one base register plus immediates.
+// No per-frame masking: padded frames have z = 0, add nothing to the scatter
+// sums, and their gamma is subtracted analytically by the caller.
+template <int D, int K, typename CT>
+__device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int g, int st, int nsteps, int lane, int& buf,
+                                           double eps, double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K],
+                                           int j0 = 0) {
+  using G = GroupDims<D>;
+  constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
+  const CT* __restrict__ zrow = &sm.zbuf[st][2 * g][0] + lane + 32 * j0;
+  const double* __restrict__ cg = &sm.coef[0][g * NSG];
+#pragma unroll 1
+  for (int j = 0; j < nsteps; ++j, zrow += 32) {
+    double2 x[NLOC];
+#pragma unroll
+    for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zrow + l * kStageFrames);
+    double psi[NSG];
+    group_psi<D>(x, psi);
+    // this group's share of the K quadratic forms: 2K independent FMA chains
+    double p0[K], p1[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { p0[k] = 0.0; p1[k] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NSG; i += 2) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double2 cc = *reinterpret_cast<const double2*>(cg + k * NS + i);
+        p0[k] = fma(cc.x, psi[i], p0[k]);
+        p1[k] = fma(cc.y, psi[i + 1], p1[k]);
       }
     }
-    if (HALF) {
+    double* __restrict__ xw = &sm.xq[buf][g][0][lane];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const double2 u = x[h], v = x[2 + 2 * NFULL + h];
-        psi[4 + 8 * NFULL + 2 * h] = u.x * v.x + u.y * v.y;
-        psi[4 + 8 * NFULL + 2 * h + 1] = u.x * v.y - u.y * v.x;
+    for (int k = 0; k < K; ++k) xw[k * 32] = p0[k] + p1[k];
+    __syncthreads();
+    const double* __restrict__ xr = &sm.xq[buf][0][0][lane];
+    double q[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double v = xr[k * 32];
+#pragma unroll
+      for (int gg = 1; gg < M; ++gg) v += xr[(gg * 2 * K + k) * 32];
+      q[k] = fabs(v);
+    }
+    buf ^= 1;
+    double gam[K], cw[K];
+    softmax_product<D, K>(q, sm.ew, eps, gam, cw);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sg[k] += gam[k];
+#pragma unroll
+      for (int i = 0; i < NSG; ++i) acc[k * NSG + i] = fma(cw[k], psi[i], acc[k * NSG + i]);
+    }
+  }
+}
+
+// Same as lean_chunk with TWO frames per lane and step (frames t and t + 32):
+// the coefficient loads, the barrier and the loop overhead are shared by the two
+// frames, and their E-step / softmax dependency chains interleave, which is what
+// keeps the fp64 pipe busy with only two warps per scheduler.
+template <int D, int K, typename CT>
+__device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int g, int st, int nsteps2, int lane,
+                                            int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
+                                            double (&sg)[K]) {
+  using G = GroupDims<D>;
+  constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
+  const CT* __restrict__ zrow = &sm.zbuf[st][2 * g][0] + lane;
+  const double* __restrict__ cg = &sm.coef[0][g * NSG];
+#pragma unroll 1
+  for (int j = 0; j < nsteps2; ++j, zrow += 64) {
+    double psiA[NSG], psiB[NSG];
+    {
+      double2 x[NLOC];
+#pragma unroll
+      for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zrow + l * kStageFrames);
+      group_psi<D>(x, psiA);
+#pragma unroll
+      for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zrow + l * kStageFrames + 32);
+      group_psi<D>(x, psiB);
+    }
+    double pA0[K], pA1[K], pB0[K], pB1[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { pA0[k] = 0.0; pA1[k] = 0.0; pB0[k] = 0.0; pB1[k] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NSG; i += 2) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double2 cc = *reinterpret_cast<const double2*>(cg + k * NS + i);
+        pA0[k] = fma(cc.x, psiA[i], pA0[k]);
+        pB0[k] = fma(cc.x, psiB[i], pB0[k]);
+        pA1[k] = fma(cc.y, psiA[i + 1], pA1[k]);
+        pB1[k] = fma(cc.y, psiB[i + 1], pB1[k]);
+      }
+    }
+    double* __restrict__ xw = &sm.xq[buf][g][0][lane];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      xw[k * 32] = pA0[k] + pA1[k];
+      xw[(K + k) * 32] = pB0[k] + pB1[k];
+    }
+    __syncthreads();
+    const double* __restrict__ xr = &sm.xq[buf][0][0][lane];
+    double qA[K], qB[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double va = xr[k * 32], vb = xr[(K + k) * 32];
+#pragma unroll
+      for (int gg = 1; gg < M; ++gg) {
+        va += xr[(gg * 2 * K + k) * 32];
+        vb += xr[(gg * 2 * K + K + k) * 32];
+      }
+      qA[k] = fabs(va);
+      qB[k] = fabs(vb);
+    }
+    buf ^= 1;
+    double gA[K], cA[K], gB[K], cB[K];
+    softmax_product<D, K>(qA, sm.ew, eps, gA, cA);
+    softmax_product<D, K>(qB, sm.ew, eps, gB, cB);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      sg[k] += gA[k] + gB[k];
+#pragma unroll
+      for (int i = 0; i < NSG; ++i) {
+        acc[k * NSG + i] = fma(cA[k], psiA[i], acc[k * NSG + i]);
+        acc[k * NSG + i] = fma(cB[k], psiB[i], acc[k * NSG + i]);
       }
     }
   }
-};
+}
 
+// General posterior (log domain or qmin-ratio form) with the reference's floors.
 template <int D, int K>
-__device__ __forceinline__ void persist_softmax(const double (&q)[K], const double* __restrict__ ld,
+__device__ __forceinline__ void softmax_general(const double (&q)[K], const double* __restrict__ ld,
                                                 const double* __restrict__ w, const double* __restrict__ ew,
                                                 bool fast, double eps, double (&gam)[K], double (&invq)[K]) {
   double a[K];
@@ -199,7 +382,7 @@ __device__ __forceinline__ void persist_softmax(const double (&q)[K], const doub
   double den = a[0];
 #pragma unroll
   for (int k = 1; k < K; ++k) den += a[k];
-  const double inv = fast_rcp(fmax(den, kTiny));
+  const double inv = 1.0 / fmax(den, kTiny);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double g = a[k] * inv;
@@ -208,57 +391,142 @@ __device__ __forceinline__ void persist_softmax(const double (&q)[K], const doub
   }
 }
 
+// General step (runtime group index): M-step-only iteration 0, and the FULL
+// variant (saliency, source activity mask, log-domain softmax).  Frames are
+// masked individually.
+template <int D, int K, typename CT, bool FULL>
+__device__ __forceinline__ void general_chunk(const PersistArgs& a, PersistSmem<D, K, CT>& sm, int g, int bin,
+                                              int st, int t_chunk, int nsteps, int lane, int& buf, bool mstep_only,
+                                              bool fast, double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K]) {
+  using G = GroupDims<D>;
+  constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
+  const int T = a.T;
+  const CT* __restrict__ zb = &sm.zbuf[st][0][0];
+  const CT* __restrict__ zg = zb + 2 * g * kStageFrames + lane;
+#pragma unroll 1
+  for (int j = 0; j < nsteps; ++j) {
+    const int t = t_chunk + j * 32 + lane;
+    const bool valid = t < T;
+    const int tc = valid ? t : 0;
+    double2 x[NLOC];
+#pragma unroll
+    for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zg + l * kStageFrames + j * 32);
+    double psi[NSG];
+    group_psi<D>(x, psi);
+    double gam[K], invq[K];
+    bool done = false;
+    if constexpr (FULL) {
+      if (!mstep_only) {
+        const double* __restrict__ cg = &sm.coef[0][g * NSG];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          double pq = 0.0;
+#pragma unroll
+          for (int i = 0; i < NSG; ++i) pq = fma(cg[k * NS + i], psi[i], pq);
+          sm.xq[buf][g][k][lane] = pq;
+        }
+        __syncthreads();
+        double q[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          double v = sm.xq[buf][0][k][lane];
+#pragma unroll
+          for (int gg = 1; gg < M; ++gg) v += sm.xq[buf][gg][k][lane];
+          q[k] = fmax(fabs(v), 10.0 * kTiny);
+        }
+        buf ^= 1;
+        if (a.activity != nullptr) {
+          // masked classes get zero posterior mass (mixture_model_utils.py:39-41)
+          double ewm[K], wm[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const bool on = a.activity[((size_t)bin * K + k) * T + tc] != 0;
+            ewm[k] = on ? sm.ew[k] : 0.0;
+            wm[k] = on ? sm.w[k] : 0.0;
+          }
+          softmax_general<D, K>(q, sm.ld, wm, ewm, fast, a.aff_eps, gam, invq);
+        } else {
+          softmax_general<D, K>(q, sm.ld, sm.w, sm.ew, fast, a.aff_eps, gam, invq);
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        gam[k] = a.aff_in[((size_t)bin * K + k) * T + tc];
+        invq[k] = 1.0;
+      }
+    }
+    double sal = 1.0;
+    if (FULL && a.saliency != nullptr) sal = a.saliency[(size_t)bin * T + tc];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double gs = valid ? gam[k] * sal : 0.0;
+      const double cw = gs * invq[k];
+      sg[k] += gs;
+#pragma unroll
+      for (int i = 0; i < NSG; ++i) acc[k * NSG + i] = fma(cw, psi[i], acc[k * NSG + i]);
+    }
+  }
+}
+
 // In-place inverse of a Hermitian positive definite D x D matrix in shared
-// memory by Gauss-Jordan elimination without pivoting (one warp).  Returns
-// log det; *ok is false if a pivot is not positive / finite.
+// memory by Gauss-Jordan elimination without pivoting (one warp; every lane
+// keeps its own entries in registers and only fetches the pivot row / column).
+// Returns det(A) as the product of the pivots (the caller takes one log);
+// *ok is false if a pivot is not positive / finite.
 template <int D>
 __device__ __forceinline__ double warp_hpd_inverse(double2* __restrict__ A, int lane, bool* ok) {
   constexpr int NS = D * D;
   constexpr int PER = (NS + 31) / 32;
-  double ldet = 0.0;
+  int ri[PER], ci[PER];
+  double2 mine[PER];
+#pragma unroll
+  for (int r = 0; r < PER; ++r) {
+    const int idx = lane + 32 * r;
+    ri[r] = idx / D;
+    ci[r] = idx - ri[r] * D;
+    mine[r] = idx < NS ? A[idx] : make_double2(0.0, 0.0);
+  }
+  double det = 1.0;
   bool good = true;
 #pragma unroll 1
   for (int j = 0; j < D; ++j) {
     const double p = A[j * D + j].x;
-    good = good && (p > 0.0) && isfinite(p);
-    const double ip = 1.0 / p;
-    ldet += log(p);
-    double2 nv[PER];
+    good = good && (p > 0.0) && (p < 1e300);
+    const double ip = fast_rcp(p);
+    det *= p;
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
-      const int idx = lane + 32 * r;
-      if (idx < NS) {
-        const int i = idx / D, k = idx - i * D;
-        const double2 aik = A[idx], aij = A[i * D + j], ajk = A[j * D + k];
-        double2 v;
+      if (lane + 32 * r < NS) {
+        const int i = ri[r], k = ci[r];
+        const double2 aij = A[i * D + j], ajk = A[j * D + k];
+        const double sx = aij.x * ip, sy = aij.y * ip;  // a_ij / p
+        // general entry: a_ik - a_ij a_jk / p
+        double2 v = make_double2(mine[r].x - (sx * ajk.x - sy * ajk.y), mine[r].y - (sx * ajk.y + sy * ajk.x));
+        if (k == j) v = make_double2(-sx, -sy);
+        if (i == j) v = make_double2(ajk.x * ip, ajk.y * ip);
         if (i == j && k == j) v = make_double2(ip, 0.0);
-        else if (i == j) v = make_double2(ajk.x * ip, ajk.y * ip);
-        else if (k == j) v = make_double2(-aij.x * ip, -aij.y * ip);
-        else {
-          const double tr = (aij.x * ajk.x - aij.y * ajk.y) * ip, ti = (aij.x * ajk.y + aij.y * ajk.x) * ip;
-          v = make_double2(aik.x - tr, aik.y - ti);
-        }
-        nv[r] = v;
+        mine[r] = v;
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < PER; ++r) {
-      const int idx = lane + 32 * r;
-      if (idx < NS) A[idx] = nv[r];
-    }
+    for (int r = 0; r < PER; ++r)
+      if (lane + 32 * r < NS) A[lane + 32 * r] = mine[r];
     __syncwarp();
   }
   *ok = good;
-  return ldet;
+  return det;
 }
 
-template <int D, int K, typename CT, bool FULL>
-__global__ void __launch_bounds__(32 * (D / 2), (D == 8 ? 3 : (D == 6 ? 4 : 6)))
+template <int D, int K, typename CT, bool FULL, int FPL>
+__global__ void __launch_bounds__(32 * (D / 2), (FPL == 2 ? (D == 8 ? 2 : (D == 6 ? 2 : 4)) : (D == 8 ? 3 : (D == 6 ? 4 : 6))))
 em_persistent_kernel(const PersistArgs a) {
   using SM = PersistSmem<D, K, CT>;
-  using ST = PersistStep<D, K, CT, FULL>;
-  constexpr int NS = D * D, M = D / 2, NSG = ST::NSG, NLOC = ST::NLOC;
+  using G = GroupDims<D>;
+  constexpr int NS = D * D, M = D / 2, NSG = G::NSG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
@@ -282,17 +550,12 @@ em_persistent_kernel(const PersistArgs a) {
     const int t0 = c * kStageFrames;
     const int nf = min(kStageFrames, zs - t0);
     const uint32_t bytes = (uint32_t)nf * sizeof(CT);
-    mbar_expect_tx(&sm.full[st], bytes * D);
+    mbar_expect_tx(&sm.full[st], bytes * SM::ROWS);
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      bulk_g2s(&sm.zbuf[st][d][0], zbase + ((size_t)bin * D + d) * zs + t0, bytes, &sm.full[st]);
+    for (int r = 0; r < SM::ROWS; ++r)
+      bulk_g2s(&sm.zbuf[st][r][0], zbase + ((size_t)bin * D + row_channel(D, r)) * zs + t0, bytes, &sm.full[st]);
   };
   if (tid == 0 && cur < total) issue_chunk(cur % F, 0, 0);
-
-  // per-warp constants: channel offsets of the group's local channels
-  int choff[NLOC];
-#pragma unroll
-  for (int l = 0; l < NLOC; ++l) choff[l] = group_channel(D, g, l) * kStageFrames;
 
   while (cur < total) {
     const int it = cur / F, bin = cur - it * F;
@@ -305,7 +568,7 @@ em_persistent_kernel(const PersistArgs a) {
       }
     }
     __syncthreads();
-    const int nxt = sm.tick[1];
+    const int nxt = sm.tick[1];  // read before any later barrier; rewritten only after them
     if (!mstep_only) {
       const double* __restrict__ cf = a.coef + (size_t)bin * K * NS;
       for (int i = tid; i < K * NS; i += blockDim.x) (&sm.coef[0][0])[i] = __ldcg(cf + i);
@@ -316,6 +579,7 @@ em_persistent_kernel(const PersistArgs a) {
       }
     }
     const bool fast = FULL ? (a.softmax_fast && !(a.user_model && it == 0)) : true;
+    const bool lean = !FULL && !mstep_only;
 
     double acc[K * NSG];
 #pragma unroll
@@ -335,74 +599,29 @@ em_persistent_kernel(const PersistArgs a) {
       const int st = chunk_cnt & 1u;
       mbar_wait(&sm.full[st], (chunk_cnt >> 1) & 1u);
       ++chunk_cnt;
-      const CT* __restrict__ zb = &sm.zbuf[st][0][0];
       const int t_chunk = c * kStageFrames;
       const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
-#pragma unroll 1
-      for (int j = 0; j < nsteps; ++j) {
-        const int t = t_chunk + j * 32 + lane;
-        const bool valid = t < T;
-        double2 x[NLOC];
-#pragma unroll
-        for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zb + choff[l] + j * 32 + lane);
-        double psi[NSG];
-        ST::psi_of(x, psi);
-        double gam[K], invq[K];
-        if (!mstep_only) {
-          const double* __restrict__ cg = &sm.coef[0][g * NSG];
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            double pq = 0.0;
-#pragma unroll
-            for (int i = 0; i < NSG; i += 2) {
-              const double2 cc = *reinterpret_cast<const double2*>(cg + k * NS + i);
-              pq = fma(cc.x, psi[i], pq);
-              pq = fma(cc.y, psi[i + 1], pq);
-            }
-            sm.xq[buf][g][k][lane] = pq;
-          }
-          __syncthreads();
-          double q[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            double v = sm.xq[buf][0][k][lane];
-#pragma unroll
-            for (int gg = 1; gg < M; ++gg) v += sm.xq[buf][gg][k][lane];
-            q[k] = fmax(fabs(v), 10.0 * kTiny);
-          }
-          buf ^= 1;
-          if (FULL && a.activity != nullptr) {
-            // masked classes get zero posterior mass (mixture_model_utils.py:39-41):
-            // fold the mask into the class weights of this frame
-            double ewm[K], wm[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              const bool on = a.activity[((size_t)bin * K + k) * T + (valid ? t : 0)] != 0;
-              ewm[k] = on ? sm.ew[k] : 0.0;
-              wm[k] = on ? sm.w[k] : 0.0;
-            }
-            persist_softmax<D, K>(q, sm.ld, wm, ewm, fast, a.aff_eps, gam, invq);
-          } else {
-            persist_softmax<D, K>(q, sm.ld, sm.w, sm.ew, fast, a.aff_eps, gam, invq);
+      if (lean) {
+        if constexpr (FPL == 2) {
+          lean_chunk2<D, K, CT>(sm, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
+          if (nsteps & 1) {  // odd tail step of a short last chunk
+            lean_chunk<D, K, CT>(sm, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
           }
         } else {
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            gam[k] = a.aff_in[((size_t)bin * K + k) * T + (valid ? t : 0)];
-            invq[k] = 1.0;
-          }
-        }
-        double sal = 1.0;
-        if (FULL && a.saliency != nullptr) sal = a.saliency[(size_t)bin * T + (valid ? t : 0)];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const double gs = valid ? (FULL ? gam[k] * sal : gam[k]) : 0.0;
-          const double cw = gs * invq[k];
-          sg[k] += gs;
-#pragma unroll
-          for (int i = 0; i < NSG; ++i) acc[k * NSG + i] = fma(cw, psi[i], acc[k * NSG + i]);
+          lean_chunk<D, K, CT>(sm, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
         }
       }
+      else general_chunk<D, K, CT, FULL>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
+    }
+    if (lean && zs > T) {
+      // the zs - T padded frames of every row behaved like zero observations
+      double q1[K], gp[K], cp[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) q1[k] = 0.0;
+      softmax_product<D, K>(q1, sm.ew, a.aff_eps, gp, cp);
+      const int npad_lane = (lane >= 32 - (zs - T)) ? 1 : 0;  // zs - T < 32: last step's tail lanes
+#pragma unroll
+      for (int k = 0; k < K; ++k) sg[k] -= npad_lane ? gp[k] : 0.0;
     }
 
     // ---- reduce the 32 frames of each warp; group g owns slots [g*NSG, (g+1)*NSG) ----
@@ -458,7 +677,8 @@ em_persistent_kernel(const PersistArgs a) {
         for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
         __syncwarp();
         bool ok;
-        double ldk = warp_hpd_inverse<D>(A, lane, &ok);
+        const double det = warp_hpd_inverse<D>(A, lane, &ok);
+        double ldk = log(det);
         double tinv = 0.0;
         for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
         tinv = warp_sum(tinv);
@@ -499,7 +719,6 @@ em_persistent_kernel(const PersistArgs a) {
         }
         if (lane == 0) sm.ld[k] = ldk;
       }
-      __threadfence();
       __syncthreads();
       if (tid < K) {
         const int k = tid;
@@ -516,10 +735,14 @@ em_persistent_kernel(const PersistArgs a) {
         a.w[(size_t)bin * K + k] = wk;
         a.ld[(size_t)bin * K + k] = sm.ld[k];
         a.ew[(size_t)bin * K + k] = wk * exp(ldmin - sm.ld[k]);
-        __threadfence();
       }
+      // CTA barrier, then ONE gpu-scope release by thread 0 (the cooperative-groups grid-sync
+      // pattern): the barrier orders every thread's model stores before the cumulative release.
       __syncthreads();
-      if (tid == 0) st_release_gpu(a.flags + bin, it + 1);
+      if (tid == 0) {
+        __threadfence();
+        st_release_gpu(a.flags + bin, it + 1);
+      }
     }
     cur = nxt;
   }
