@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpbb.so')
+# PBB_LIB selects an alternative build of the same ABI (kernel-variant experiments)
+LIB_PATH = os.environ.get('PBB_LIB') or os.path.join(_HERE, 'libpbb.so')
 
 PBB_C64, PBB_C128 = 0, 1
 NORM_NONE, NORM_EIGENVALUE, NORM_TRACE = 0, 1, 2

@@ -4,7 +4,21 @@
 
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
+#include "em_quad.cuh"
 #include "prof.cuh"
+
+#ifndef PBB_QUAD_FPL
+#define PBB_QUAD_FPL 1
+#endif
+#ifndef PBB_QUAD_CREG
+#define PBB_QUAD_CREG false
+#endif
+#ifndef PBB_LEAN_KERNEL
+#define PBB_LEAN_KERNEL 0  // 0: slot-group-per-warp kernel (em_persistent.cuh), 1: quad-lane kernel (em_quad.cuh)
+#endif
+#ifndef PBB_CTA_FPL
+#define PBB_CTA_FPL 2
+#endif
 
 namespace pbb {
 
@@ -39,6 +53,7 @@ struct CacgmmWorkspace {
   int zs;       // padded row stride of z (frames)
   int* flags;   // (F) per-bin model version, persistent kernel
   int* ticket;  // (1)
+  unsigned long long* phase;  // (16) debug phase counters
   double* part;
   double* coef;
   double* ld;
@@ -57,7 +72,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return o; };
   const int zs = (T + 31) / 32 * 32;
   const size_t o_z = take((size_t)F * D * zs * sizeof(double2));
-  const size_t o_flags = take((size_t)(F + 1) * sizeof(int));
+  const size_t o_flags = take((size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8);
   const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
   const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
   const size_t o_ld = take((size_t)F * K * sizeof(double));
@@ -69,6 +84,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   ws.zs = zs;
   ws.flags = reinterpret_cast<int*>(b + o_flags);
   ws.ticket = ws.flags + F;
+  ws.phase = reinterpret_cast<unsigned long long*>(b + o_flags + (((size_t)(F + 1) * sizeof(int) + 7) / 8) * 8);
   ws.part = reinterpret_cast<double*>(b + o_part);
   ws.coef = reinterpret_cast<double*>(b + o_coef);
   ws.ld = reinterpret_cast<double*>(b + o_ld);
@@ -183,36 +199,50 @@ static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
 }
 
 // ---- persistent kernel launch ---------------------------------------------------
-template <int D, int K, typename CT, bool FULL>
-static int launch_persist_t(const PersistArgs& a, cudaStream_t st) {
-  // lean variant: two frames per lane and step (255 registers, 2 CTAs/SM)
-  auto kern = em_persistent_kernel<D, K, CT, FULL, FULL ? 1 : 2>;
-  const size_t smem = sizeof(PersistSmem<D, K, CT>);
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
+template <typename Kern>
+static int launch_persistent_generic(Kern kern, int threads, size_t smem, int* cache, const PersistArgs& a,
+                                     const char* name, cudaStream_t st) {
+  if (*cache == 0) {
     PBB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n = 0;
-    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 32 * (D / 2), smem));
-    if (n < 1) { set_error("persistent EM kernel does not fit on this device"); return 1; }
-    ctas_per_sm = n;
+    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem));
+    if (n < 1) { set_error("%s does not fit on this device", name); return 1; }
+    *cache = n;
   }
   int dev = 0, sms = 0;
   PBB_CUDA(cudaGetDevice(&dev));
   PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = (long long)ctas_per_sm * sms;
+  long long grid = (long long)(*cache) * sms;
   const long long tasks = (long long)a.iterations * a.F;
   if (grid > tasks) grid = tasks;
-  LaunchScope ls("em_persistent_kernel", st);
-  kern<<<(unsigned)grid, 32 * (D / 2), smem, st>>>(a);
+  LaunchScope ls(name, st);
+  kern<<<(unsigned)grid, threads, smem, st>>>(a);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
 
+// full = saliency / activity mask / log-domain softmax: slot-group-per-warp kernel (em_persistent.cuh);
+// lean = quad-lane kernel (em_quad.cuh), two frames per lane
+template <int D, int K, typename CT>
+static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
+  static int cache_full = 0, cache_lean = 0;
+  if (full)
+    return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, 32 * (D / 2),
+                                     sizeof(PersistSmem<D, K, CT>), &cache_full, a, "em_persistent_kernel", st);
+#if PBB_LEAN_KERNEL == 1
+  constexpr int FPL = PBB_QUAD_FPL;
+  return launch_persistent_generic(em_quad_kernel<D, K, CT, FPL, PBB_QUAD_CREG>, 32 * kQuadWarps, sizeof(QuadSmem<D, K, CT>),
+                                   &cache_lean, a, "em_quad_kernel", st);
+#else
+  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL>, 32 * (D / 2),
+                                   sizeof(PersistSmem<D, K, CT>), &cache_lean, a, "em_persistent_kernel", st);
+#endif
+}
+
 template <int D, int K>
 static int launch_persist_dk(const PersistArgs& a, int dtype, bool full, cudaStream_t st) {
-  if (dtype == PBB_C128)
-    return full ? launch_persist_t<D, K, double2, true>(a, st) : launch_persist_t<D, K, double2, false>(a, st);
-  return full ? launch_persist_t<D, K, float2, true>(a, st) : launch_persist_t<D, K, float2, false>(a, st);
+  if (dtype == PBB_C128) return launch_persist_t<D, K, double2>(a, full, st);
+  return launch_persist_t<D, K, float2>(a, full, st);
 }
 
 template <int D>
@@ -316,7 +346,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   const bool fast_sm = softmax_fast_ok(D, opt);
   if (fast_shape(D, K) && !(opt->reserved & 1)) {
     // ---- persistent path: every EM iteration in one launch (em_persistent.cuh) ----
-    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int), st));
+    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
     if (init_aff == nullptr) {
       FromEigArgs fe;
       fe.F = F; fe.D = D; fe.K = K;
@@ -337,10 +367,22 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     p.covariance_norm = opt->covariance_norm; p.weight_mode = opt->weight_mode;
     p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
+    p.phase = ws.phase;
     // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
     const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
     const bool full = saliency != nullptr || activity != nullptr || !lean_ok || p.user_model;
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
+#ifdef PBB_PHASE_TIMING
+    {
+      unsigned long long ph[8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
+      unsigned long long tot = 0;
+      for (int i = 0; i < 7; ++i) tot += ph[i];
+      static const char* nm[7] = {"ticket+flag", "stage/chunk-barrier", "tma-wait", "em-steps", "reduce", "update", "publish"};
+      for (int i = 0; i < 7; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%\n", nm[i], 100.0 * ph[i] / (double)tot);
+    }
+#endif
     u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model
     return launch_update(u, st);
   }

@@ -35,6 +35,12 @@
 
 namespace pbb {
 
+#ifdef PBB_PHASE_TIMING
+#define PBB_PH(i) do { if (tid == 0) { long long _t = clock64(); atomicAdd(&a.phase[i], (unsigned long long)(_t - _tp)); _tp = _t; } } while (0)
+#else
+#define PBB_PH(i) do { } while (0)
+#endif
+
 struct PersistArgs {
   const void* z;   // (F, D, zs) unit-norm observation, rows zero padded to zs
   int zs;          // row stride in frames, multiple of 32
@@ -58,6 +64,7 @@ struct PersistArgs {
   int* flags;    // (F) number of model updates published for the bin
   int* ticket;   // (1)
   int* status;
+  unsigned long long* phase;  // debug: per-phase cycle sums (PBB_PHASE_TIMING builds)
 };
 
 // ---- PTX helpers --------------------------------------------------------------
@@ -545,18 +552,21 @@ em_persistent_kernel(const PersistArgs a) {
   int cur = sm.tick[0];
   unsigned chunk_cnt = 0;  // chunks consumed so far by this CTA (ring position)
 
-  auto issue_chunk = [&](int bin, int c, unsigned n) {  // thread 0 only
+  auto issue_chunk = [&](int bin, int c, unsigned n) {  // warp 0: lane r copies staged row r
     const int st = n & 1u;
     const int t0 = c * kStageFrames;
     const int nf = min(kStageFrames, zs - t0);
     const uint32_t bytes = (uint32_t)nf * sizeof(CT);
-    mbar_expect_tx(&sm.full[st], bytes * SM::ROWS);
-#pragma unroll
-    for (int r = 0; r < SM::ROWS; ++r)
-      bulk_g2s(&sm.zbuf[st][r][0], zbase + ((size_t)bin * D + row_channel(D, r)) * zs + t0, bytes, &sm.full[st]);
+    if (lane == 0) mbar_expect_tx(&sm.full[st], bytes * SM::ROWS);
+    if (lane < SM::ROWS)
+      bulk_g2s(&sm.zbuf[st][lane][0], zbase + ((size_t)bin * D + row_channel(D, lane)) * zs + t0, bytes,
+               &sm.full[st]);
   };
-  if (tid == 0 && cur < total) issue_chunk(cur % F, 0, 0);
+  if (g == 0 && cur < total) issue_chunk(cur % F, 0, 0);
 
+#ifdef PBB_PHASE_TIMING
+  long long _tp = clock64();
+#endif
   while (cur < total) {
     const int it = cur / F, bin = cur - it * F;
     const bool mstep_only = a.first_is_m && it == 0;
@@ -568,6 +578,7 @@ em_persistent_kernel(const PersistArgs a) {
       }
     }
     __syncthreads();
+    PBB_PH(0);  // ticket + flag wait
     const int nxt = sm.tick[1];  // read before any later barrier; rewritten only after them
     if (!mstep_only) {
       const double* __restrict__ cf = a.coef + (size_t)bin * K * NS;
@@ -589,15 +600,21 @@ em_persistent_kernel(const PersistArgs a) {
     for (int k = 0; k < K; ++k) sg[k] = 0.0;
     int buf = 0;
 
+    __syncthreads();  // model staged
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
-      __syncthreads();  // previous chunk fully consumed (and model staged): its stage may be refilled
-      if (tid == 0) {
+      // The stage refilled below was last read in the previous chunk.  In the E+M loops every
+      // observation load of a step precedes that step's exchange barrier, so once warp 0 is
+      // here all warps are done with it; only the M-step-only loop (no exchange) needs a barrier.
+      if (!lean) __syncthreads();
+      if (g == 0) {
         if (c + 1 < nchunks) issue_chunk(bin, c + 1, chunk_cnt + 1);
         else if (nxt < total) issue_chunk(nxt % F, 0, chunk_cnt + 1);
       }
       const int st = chunk_cnt & 1u;
+      PBB_PH(1);  // staging / chunk barrier
       mbar_wait(&sm.full[st], (chunk_cnt >> 1) & 1u);
+      PBB_PH(2);  // TMA wait
       ++chunk_cnt;
       const int t_chunk = c * kStageFrames;
       const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
@@ -612,6 +629,7 @@ em_persistent_kernel(const PersistArgs a) {
         }
       }
       else general_chunk<D, K, CT, FULL>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
+      PBB_PH(3);  // EM steps
     }
     if (lean && zs > T) {
       // the zs - T padded frames of every row behaved like zero observations
@@ -644,6 +662,7 @@ em_persistent_kernel(const PersistArgs a) {
       if (g == 0 && lane == 0) sm.S[k][NS] = v;
     }
     __syncthreads();
+    PBB_PH(4);  // reduce
 
     if (last_it) {
       // leave the raw sums for cacg_update_kernel (reference-exact eigendecomposition)
@@ -720,6 +739,7 @@ em_persistent_kernel(const PersistArgs a) {
         if (lane == 0) sm.ld[k] = ldk;
       }
       __syncthreads();
+      PBB_PH(5);  // update (Gauss-Jordan)
       if (tid < K) {
         const int k = tid;
         double wk;
@@ -739,10 +759,8 @@ em_persistent_kernel(const PersistArgs a) {
       // CTA barrier, then ONE gpu-scope release by thread 0 (the cooperative-groups grid-sync
       // pattern): the barrier orders every thread's model stores before the cumulative release.
       __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release_gpu(a.flags + bin, it + 1);
-      }
+      if (tid == 0) st_release_gpu(a.flags + bin, it + 1);
+      PBB_PH(6);  // weights + publish
     }
     cur = nxt;
   }
