@@ -138,12 +138,94 @@ int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K,
                      void* stream);
 
 /* ------------------------------------------------------------------------
+ * Complex Watson mixture model (pb_bss/distribution/cwmm.py, complex_watson.py).
+ *
+ * Device model: mode (F, K, D) complex128, concentration (F, K), weight (F, K)
+ * = CWMM.weight / complex_watson.mode / .concentration (cwmm.py:21-24).
+ * The inverse hypergeometric ratio is the quadratic B-spline of
+ * ComplexWatsonTrainer.spline (complex_watson.py:237-256); the caller builds
+ * it once with the reference's recipe and passes its knots spline_t[n + 3]
+ * and coefficients spline_c[n] (device pointers); it is model state, like the
+ * reference's cached_property. */
+size_t pbb_cwmm_workspace_bytes(int F, int T, int D, int K);
+
+/* CWMMTrainer.fit / _fit / _m_step (cwmm.py:76-240), affiliation_eps = 0.
+ * init_aff (F, K, T) is required (cwmm.py:121-127 draws it on the host). */
+int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K,
+                 const double* init_aff, const double* saliency,
+                 int iterations, int weight_mode, const double* spline_t,
+                 const double* spline_c, int spline_n,
+                 double max_concentration, void* mode, double* concentration,
+                 double* weight, void* workspace, size_t workspace_bytes,
+                 int* status, void* stream);
+
+/* CWMM.predict (cwmm.py:26-52): affiliation (F, K, T) out. weight may be NULL (1/K). */
+int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K,
+                     const void* mode, const double* concentration,
+                     const double* weight, double* affiliation,
+                     void* workspace, size_t workspace_bytes, int* status,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
  * Batched Hermitian eigendecomposition, ascending eigenvalues
  * (np.linalg.eigh as used in complex_angular_central_gaussian.py:95 and
  * pb_bss/utils.py:154).  a: (n, D, D) complex128 (only read), w: (n, D),
  * v: (n, D, D) complex128, columns are eigenvectors. */
 int pbb_heig_batched(const void* a, int n, int D, double* w, void* v,
                      int* status, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Beamforming side (pb_bss/extraction/beamformer.py).  All small matrices and
+ * vectors are complex128; the observation may be complex64 or complex128.
+ */
+
+/* get_power_spectral_density_matrix (beamformer.py:59-160) for observation
+ * (F, D, T) and mask (F, K, T) float64 (or NULL: plain average over time,
+ * K must be 1).  normalize: divide by max(sum_t mask, 1e-10) (:127-131).
+ * psd: (F, K, D, D). */
+size_t pbb_psd_workspace_bytes(int F, int T, int D, int K);
+int pbb_power_spectral_density(const void* observation, int dtype, int F,
+                               int D, int T, const double* mask, int K,
+                               int normalize, void* psd, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/* get_gev_vector (beamformer.py:292-411): eigenvector of the largest
+ * generalised eigenvalue of (target, noise), normalised like LAPACK zhegvd
+ * ITYPE=1 (w^H noise w = 1).  Replaces _c_get_gev_vector
+ * (cythonized/get_gev_vector.pyx:42-150); unlike it, matrices are row-major
+ * (n, D, D).  status = 1 + index of the first pair whose noise matrix is not
+ * positive definite (the Cython code raises ValueError there, :130-147). */
+int pbb_gev_batched(const void* target_psd, const void* noise_psd, int n,
+                    int D, void* w, int* status, void* stream);
+
+/* np.linalg.solve for a batch: a (n, D, D), b (n, D, R) -> x (n, D, R), partial
+ * pivoting.  hermitize != 0 solves with (a + a^H) / 2.  status flags singular
+ * matrices (the reference falls back to lstsq, math/solve.py:95-114). */
+int pbb_solve_batched(const void* a, const void* b, int n, int D, int R,
+                      int hermitize, void* x, int* status, void* stream);
+
+/* get_mvdr_vector (beamformer.py:230-260): w = N^-1 a / (a^H N^-1 a) with the
+ * noise PSD hermitised first.  atf (n, D), noise_psd (n, D, D), w (n, D);
+ * scratch: n * D complex128. */
+int pbb_mvdr(const void* atf, const void* noise_psd, int n, int D, void* w,
+             void* scratch, int* status, void* stream);
+
+/* Pieces of get_mvdr_vector_souden (beamformer.py:601-698): phi = solve(noise,
+ * target) -> mat = phi / max(trace(phi).real, eps) and, for every candidate
+ * reference channel R, the per-bin numerator / denominator of the SNR
+ * (num, den: (n, D) complex128) and their sums over the n bins (num_sum, den_sum:
+ * (D) complex128) that get_optimal_reference_channel divides (beamformer.py:616-624). */
+int pbb_souden(const void* phi, const void* target_psd, const void* noise_psd,
+               int n, int D, double eps, void* mat, void* num, void* den,
+               void* num_sum, void* den_sum, void* stream);
+
+/* blind_analytic_normalization (beamformer.py:459-488). */
+int pbb_blind_analytic_normalization(const void* vector, const void* noise_psd,
+                                     int n, int D, void* out, void* stream);
+
+/* apply_beamforming_vector (beamformer.py:572-583): out[f][t] = sum_d conj(w[f][d]) mix[f][d][t]. */
+int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
+                                 int F, int D, int T, void* out, void* stream);
 
 #ifdef __cplusplus
 }

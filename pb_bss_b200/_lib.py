@@ -49,7 +49,19 @@ SIGNATURES = {
     'pbb_cacgmm_mstep': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                               ctypes.POINTER(CacgmmOptions), _vp, _vp, _vp,
                               _vp, _sz, _vp, _vp]),
+    'pbb_cwmm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'pbb_cwmm_fit': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d,
+                          _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    'pbb_cwmm_predict': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     'pbb_heig_batched': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    'pbb_psd_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'pbb_power_spectral_density': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    'pbb_gev_batched': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'pbb_solve_batched': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'pbb_mvdr': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    'pbb_souden': (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'pbb_blind_analytic_normalization': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'pbb_apply_beamforming_vector': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

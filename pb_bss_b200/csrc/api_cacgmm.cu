@@ -129,7 +129,7 @@ static cudaError_t launch_fast_d(const EmArgs& a, int dtype, cudaStream_t st) {
 }
 
 // Fills nch / frames_per_block and launches the EM kernel for the shape.
-static int launch_em(EmArgs a, int dtype, int frames_per_block, cudaStream_t st) {
+int launch_em(EmArgs a, int dtype, int frames_per_block, cudaStream_t st) {
   if (fast_shape(a.D, a.K)) {
     int fpb = frames_per_block > 0 ? frames_per_block : 128;
     fpb = (fpb + 31) / 32 * 32;
@@ -274,6 +274,18 @@ static int check_shape(int F, int T, int D, int K, int dtype) {
   PBB_CHECK_ARG(T > 0, 4, "T must be positive");
   PBB_CHECK_ARG(D > 1 && D < 35, 5, "need 1 < D < 35 (cacgmm.py:197,250)");
   PBB_CHECK_ARG(K > 0 && K < kMaxK, 6, "need 0 < K < 20 (cacgmm.py:249)");
+  return 0;
+}
+
+static int launch_cw_update(CwUpdArgs u, cudaStream_t st) {
+  u.warps = update_warps(u.D, u.K);
+  const size_t smem = update_smem_per_warp(u.D) * u.warps + (size_t)2 * u.K * sizeof(double) +
+                      (size_t)u.D * u.D * sizeof(int);
+  PBB_CUDA(cudaFuncSetAttribute(cw_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  const int threads = 32 * u.warps < u.K ? ((u.K + 31) / 32 * 32) : 32 * u.warps;
+  LaunchScope ls("cw_update_kernel", st);
+  cw_update_kernel<<<u.F, threads, smem, st>>>(u);
+  PBB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -502,5 +514,96 @@ int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K, const
   return launch_update(u, st);
 }
 
-}  // extern "C"
+size_t pbb_cwmm_workspace_bytes(int F, int T, int D, int K) { return pbb_cacgmm_workspace_bytes(F, T, D, K); }
 
+int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const double* init_aff,
+                 const double* saliency, int iterations, int weight_mode, const double* spline_t,
+                 const double* spline_c, int spline_n, double max_concentration, void* mode,
+                 double* concentration, double* weight, void* workspace, size_t workspace_bytes, int* status,
+                 void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  if (int r = check_shape(F, T, D, K, dtype)) return r;
+  PBB_CHECK_ARG(init_aff != nullptr, 7, "initial affiliations are null (cwmm.py:121-127)");
+  PBB_CHECK_ARG(iterations > 0, 9, "iterations must be positive");
+  PBB_CHECK_ARG(weight_mode == PBB_WEIGHT_TIME || weight_mode == PBB_WEIGHT_CONST, 10, "bad weight_mode");
+  PBB_CHECK_ARG(spline_t && spline_c && spline_n >= 3, 11, "spline table is missing");
+  PBB_CHECK_ARG(mode && concentration && weight, 15, "model output is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 18,
+                "workspace too small (pbb_cwmm_workspace_bytes)");
+  PBB_CHECK_ARG(status != nullptr, 20, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CacgmmWorkspace ws = carve(workspace, F, T, D, K);
+  PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
+  if (r) return r;
+  EmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.model_kind = 1;
+  a.coef = ws.coef; a.ld = ws.ld; a.w = weight; a.ew = ws.ew;
+  a.saliency = saliency; a.part = ws.part;
+  CwUpdArgs u;
+  memset(&u, 0, sizeof(u));
+  u.F = F; u.T = T; u.D = D; u.K = K;
+  u.part = ws.part; u.weight_mode = weight_mode;
+  u.spline.t = spline_t; u.spline.c = spline_c; u.spline.n = spline_n;
+  u.spline.max_concentration = max_concentration;
+  // domain of the interpolant: first and last knot (repeated k + 1 times)
+  // are read on the host side of the ABI by the caller; here they are fetched lazily on the device
+  u.mode = reinterpret_cast<double2*>(mode); u.concentration = concentration; u.weight = weight;
+  u.coef = ws.coef; u.ld = ws.ld; u.ew = ws.ew; u.status = status;
+  {
+    double ends[2];
+    PBB_CUDA(cudaMemcpyAsync(&ends[0], spline_t, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PBB_CUDA(cudaMemcpyAsync(&ends[1], spline_t + spline_n + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PBB_CUDA(cudaStreamSynchronize(st));
+    u.spline.x_lo = ends[0]; u.spline.x_hi = ends[1];
+  }
+  for (int it = 0; it < iterations; ++it) {
+    if (it == 0) { a.mode = kModeM; a.aff_in = init_aff; a.q_in = nullptr; }
+    else { a.mode = kModeEM; a.aff_in = nullptr; }
+    int nch = launch_em(a, dtype, 0, st);
+    if (nch <= 0) return nch ? nch : 1;
+    u.nch = nch;
+    if ((r = launch_cw_update(u, st))) return r;
+  }
+  return 0;
+}
+
+int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K, const void* mode,
+                     const double* concentration, const double* weight, double* affiliation, void* workspace,
+                     size_t workspace_bytes, int* status, void* stream) {
+  PBB_CHECK_ARG(y != nullptr, 1, "y is null");
+  if (int r = check_shape(F, T, D, K, dtype)) return r;
+  PBB_CHECK_ARG(mode && concentration, 7, "model is null");
+  PBB_CHECK_ARG(affiliation != nullptr, 10, "affiliation output is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 11,
+                "workspace too small (pbb_cwmm_workspace_bytes)");
+  PBB_CHECK_ARG(status != nullptr, 13, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CacgmmWorkspace ws = carve(workspace, F, T, D, K);
+  PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
+  if (r) return r;
+  CwFromModelArgs fm;
+  fm.F = F; fm.D = D; fm.K = K;
+  fm.mode = reinterpret_cast<const double2*>(mode); fm.concentration = concentration; fm.weight = weight;
+  fm.coef = ws.coef; fm.ld = ws.ld; fm.ew = ws.ew; fm.w = ws.w;
+  {
+    LaunchScope ls("cw_from_model_kernel", st);
+    cw_from_model_kernel<<<F, 128, (size_t)D * D * sizeof(int), st>>>(fm);
+    PBB_CUDA(cudaGetLastError());
+  }
+  EmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
+  a.mode = kModeE; a.model_kind = 1;
+  a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
+  a.aff_out = affiliation;
+  int nch = launch_em(a, dtype, 0, st);
+  return nch > 0 ? 0 : (nch ? nch : 1);
+}
+
+}  // extern "C"

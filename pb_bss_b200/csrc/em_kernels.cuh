@@ -13,34 +13,10 @@
 // quadratic form never round-trip through HBM.
 #pragma once
 #include "common.cuh"
+#include "em_args.cuh"
 #include "heig.cuh"
 
 namespace pbb {
-
-enum EmMode { kModeM = 0, kModeEM = 1, kModeE = 2 };
-
-struct EmArgs {
-  const void* z;   // (F, D, zs): rows zero padded to zs frames
-  int zs;
-  int F, T, D, K;
-  int mode;          // EmMode
-  int softmax_fast;  // integer-power softmax is safe (see em_softmax)
-  const double* coef;
-  const double* ld;
-  const double* w;
-  const double* ew;
-  const uint8_t* activity;  // (F, K, T) or null
-  double aff_eps;
-  const double* aff_in;    // (F, K, T), mode M
-  const double* q_in;      // (F, K, T) or null (= 1), mode M
-  const double* saliency;  // (F, T) or null
-  double* part;            // (F, NCH, K, NS + 1), modes M / EM
-  double* aff_out;         // (F, K, T) or null
-  double* q_out;           // (F, K, T) or null
-  double* loglik_part;     // (F, NCH) or null
-  int nch;
-  int frames_per_block;    // multiple of 32
-};
 
 template <int N> __device__ __forceinline__ double ipow(double x) {
   if constexpr (N == 1) return x;
@@ -108,6 +84,32 @@ __device__ __forceinline__ void em_softmax(const double (&q)[K], const double* _
     if (eps != 0.0) g = fmin(fmax(g, eps), 1.0 - eps);
     gam[k] = g;
   }
+}
+
+// Complex Watson posterior of one frame: log_pdf = kappa |m^H z|^2 - log c(kappa)
+// (complex_watson.py:73-87), then the same softmax (mixture_model_utils.py:7-55,
+// affiliation_eps = 0, cwmm.py:161).  q[k] = |m_k^H z|^2 arrives as the slot-form
+// quadratic form of the rank-1 matrix m m^H.
+template <int K>
+__device__ __forceinline__ void watson_softmax(const double (&q)[K], const double* __restrict__ lognorm,
+                                               const double* __restrict__ w, const double* __restrict__ kappa,
+                                               double (&gam)[K]) {
+  double lp[K];
+  double m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    lp[k] = kappa[k] * q[k] - lognorm[k];
+    m = fmax(m, lp[k]);
+  }
+  double den = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    gam[k] = exp(lp[k] - m) * w[k];
+    den += gam[k];
+  }
+  const double inv = 1.0 / fmax(den, kTiny);
+#pragma unroll
+  for (int k = 0; k < K; ++k) gam[k] *= inv;
 }
 
 // --------------------------------------------------------------------------
@@ -204,7 +206,14 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
       buf ^= 1;
       double ll;
       const uint8_t* act = a.activity ? a.activity + ((size_t)f * K) * T + (valid ? t : 0) : nullptr;
-      em_softmax<D, K>(q, sm.ld, sm.w, sm.ew, act, (size_t)T, fast, a.aff_eps, want_ll, gam, invq, ll);
+      if (a.model_kind == 1) {
+        watson_softmax<K>(q, sm.ld, sm.w, sm.ew, gam);
+#pragma unroll
+        for (int k = 0; k < K; ++k) invq[k] = 1.0;
+        ll = 0.0;
+      } else {
+        em_softmax<D, K>(q, sm.ld, sm.w, sm.ew, act, (size_t)T, fast, a.aff_eps, want_ll, gam, invq, ll);
+      }
       if (GI == 0 && valid) {
         llsum += ll;
         if (a.aff_out) {
@@ -220,7 +229,7 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const size_t o = ((size_t)f * K + k) * T + (valid ? t : 0);
-        gam[k] = a.aff_in[o];
+        gam[k] = a.aff_in ? a.aff_in[o] : 1.0;
         invq[k] = a.q_in ? 1.0 / fmax(a.q_in[o], 10.0 * kTiny) : 1.0;
       }
     }
@@ -304,7 +313,6 @@ __global__ void __launch_bounds__(32 * kEmGroups, 3) em_fast_kernel(const EmArgs
 // cross-thread reduction is needed, sums are deterministic.
 // --------------------------------------------------------------------------
 constexpr int kGenFrames = 128;  // frames per block of the generic kernel
-constexpr int kMaxK = 20;
 
 template <typename CT>
 __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) {
@@ -345,9 +353,14 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
     double lp[kMaxK];
     for (int k = 0; k < K; ++k) {
       q[k] = fmax(fabs(q[k]), kTiny);
-      lp[k] = -(double)D * log(q[k]) - a.ld[(size_t)f * K + k];
+      if (a.model_kind == 1) {
+        lp[k] = a.ew[(size_t)f * K + k] * q[k] - a.ld[(size_t)f * K + k];
+        invq[k] = 1.0;
+      } else {
+        lp[k] = -(double)D * log(q[k]) - a.ld[(size_t)f * K + k];
+        invq[k] = 1.0 / fmax(q[k], 10.0 * kTiny);
+      }
       m = fmax(m, lp[k]);
-      invq[k] = 1.0 / fmax(q[k], 10.0 * kTiny);
     }
     double se = 0.0, den = 0.0;
     for (int k = 0; k < K; ++k) {
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
   } else {
     for (int k = 0; k < K; ++k) {
       const size_t o = ((size_t)f * K + k) * T + (valid ? t : 0);
-      gam[k] = a.aff_in[o];
+      gam[k] = a.aff_in ? a.aff_in[o] : 1.0;
       invq[k] = a.q_in ? 1.0 / fmax(a.q_in[o], 10.0 * kTiny) : 1.0;
     }
   }
@@ -616,6 +629,196 @@ __global__ void cacg_from_eig_kernel(const FromEigArgs u) {
     u.w[(size_t)f * K + k] = wk;
     u.ld[(size_t)f * K + k] = ld_s[k];
     u.ew[(size_t)f * K + k] = wk * exp(ldmin - ld_s[k]);
+  }
+}
+
+// --------------------------------------------------------------------------
+// Complex Watson model update (complex_watson.py:300-315, pb_bss/utils.py:111-169):
+// covariance = S / sum(gamma), mode = eigenvector of the largest eigenvalue,
+// concentration = inverse hypergeometric ratio of that eigenvalue, evaluated on
+// the quadratic B-spline the host built with the reference's own recipe
+// (complex_watson.py:237-256): knots t[0..n+2], coefficients c[0..n-1].
+// --------------------------------------------------------------------------
+struct CwSpline {
+  const double* t;   // n + 3 knots
+  const double* c;   // n coefficients
+  int n;
+  double x_lo, x_hi;     // domain of the interpolant (first / last eigenvalue marker)
+  double max_concentration;
+};
+
+__device__ inline double cw_spline_eval(const CwSpline& sp, double x) {
+  if (!(x == x)) return x;                      // NaN in, NaN out
+  if (x < sp.x_lo) return 0.0;                  // fill_value = (0, max_concentration)
+  if (x > sp.x_hi) return sp.max_concentration;
+  const int k = 2, n = sp.n;
+  int lo = k, hi = n;  // find i in [k, n-1] with t[i] <= x < t[i+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (sp.t[mid] <= x) lo = mid; else hi = mid;
+  }
+  const int i = lo;
+  double d0 = sp.c[i - 2], d1 = sp.c[i - 1], d2 = sp.c[i];
+  // de Boor, degree 2
+  double a2 = (x - sp.t[i]) / (sp.t[i + 2] - sp.t[i]);
+  double a1 = (x - sp.t[i - 1]) / (sp.t[i + 1] - sp.t[i - 1]);
+  d2 = (1.0 - a2) * d1 + a2 * d2;
+  d1 = (1.0 - a1) * d0 + a1 * d1;
+  a2 = (x - sp.t[i]) / (sp.t[i + 1] - sp.t[i]);
+  return (1.0 - a2) * d1 + a2 * d2;
+}
+
+// log( 1F1(1; D; kappa) * 2 pi^D / (D-1)! )  (complex_watson.py:157-168).  Series
+// for small kappa, Mardia's closed form (complex_watson.py:109-138) otherwise.
+__device__ inline double cw_log_norm(double kappa, int D) {
+  double lfact = 0.0;
+  for (int r = 2; r < D; ++r) lfact += log((double)r);
+  const double base = log(2.0) + (double)D * log(3.14159265358979323846) - lfact;
+  if (kappa < 20.0) {
+    double s = 1.0, term = 1.0;
+    for (int n = 1; n < 400; ++n) {
+      term *= kappa / (double)(D + n - 1);
+      s += term;
+      if (term < 1e-17 * s) break;
+    }
+    return base + log(s);
+  }
+  double part = 0.0, pw = 1.0, fr = 1.0;  // sum_{r=0}^{D-2} kappa^r / r!
+  for (int r = 0; r <= D - 2; ++r) {
+    if (r > 0) { pw *= kappa; fr *= (double)r; }
+    part += pw / fr;
+  }
+  return log(2.0) + (double)D * log(3.14159265358979323846) + (1.0 - (double)D) * log(kappa) + kappa +
+         log1p(-exp(-kappa) * part);
+}
+
+struct CwUpdArgs {
+  int F, T, D, K;
+  int nch;
+  const double* part;   // (F, NCH, K, NS + 1)
+  int weight_mode;
+  CwSpline spline;
+  double2* mode;        // (F, K, D) out
+  double* concentration;  // (F, K) out
+  double* weight;       // (F, K) out
+  double* coef; double* ld; double* ew;  // E-step form: slots of m m^H, log norm, kappa
+  int* status;
+  int warps;
+};
+
+// slots of the rank-1 matrix m m^H
+__device__ inline void cw_coef_from_mode(const double2* __restrict__ m, const int* __restrict__ tab, int D, int lane,
+                                         double* __restrict__ coef_out) {
+  const int NS = D * D;
+  for (int s = lane; s < NS; s += 32) {
+    const int pk = tab[s];
+    const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
+    const double2 md = m[d], me = m[e];
+    const double re = md.x * me.x + md.y * me.y, im = md.y * me.x - md.x * me.y;  // m_d conj(m_e)
+    coef_out[s] = kind == 0 ? re : (kind == 1 ? 2.0 * re : -2.0 * im);
+  }
+}
+
+__global__ void cw_update_kernel(const CwUpdArgs u) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = u.D, K = u.K, NS = D * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x;
+  const size_t per_warp = update_smem_per_warp(D);
+  unsigned char* mine = smem_raw + per_warp * warp;
+  double2* A = reinterpret_cast<double2*>(mine);
+  double2* V = A + NS;
+  double* rot = reinterpret_cast<double*>(V + NS);
+  double* S = rot + ((D + 1) / 2) * 6;
+  double* sumg = reinterpret_cast<double*>(smem_raw + per_warp * u.warps);
+  int* tab = reinterpret_cast<int*>(sumg + 2 * K);
+  for (int s = threadIdx.x; s < NS; s += blockDim.x) tab[s] = slot_pack(D, s);
+  __syncthreads();
+  for (int k = warp; k < K; k += u.warps) {
+    const double* __restrict__ p0 = u.part + ((size_t)f * u.nch * K + k) * (NS + 1);
+    for (int s = lane; s <= NS; s += 32) {
+      double sum = 0.0;
+      for (int c = 0; c < u.nch; ++c) sum += p0[(size_t)c * K * (NS + 1) + s];
+      if (s < NS) S[s] = sum; else sumg[k] = sum;
+    }
+    __syncwarp();
+    const double scale = 1.0 / sumg[k];  // complex_watson.py:311-312: no floor on the denominator
+    bool bad = false;
+    double* Ad = reinterpret_cast<double*>(A);
+    for (int s = lane; s < NS; s += 32) {
+      const int pk = tab[s];
+      const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
+      const double v = S[s] * scale;
+      bad |= !isfinite(v);
+      if (kind == 0) { Ad[2 * (d * D + d)] = v; Ad[2 * (d * D + d) + 1] = 0.0; }
+      else if (kind == 1) { Ad[2 * (d * D + e)] = v; Ad[2 * (e * D + d)] = v; }
+      else { Ad[2 * (d * D + e) + 1] = -v; Ad[2 * (e * D + d) + 1] = v; }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(u.status, f + 1);
+    warp_jacobi(A, V, rot, D, lane);
+    // largest eigenvalue; ties resolved like "last of the ascending order"
+    int best = 0;
+    double lmax = A[0].x;
+    for (int d = 1; d < D; ++d) {
+      const double l = A[d * D + d].x;
+      if (l >= lmax) { lmax = l; best = d; }
+    }
+    const double kappa = cw_spline_eval(u.spline, lmax);
+    double2* __restrict__ mo = u.mode + ((size_t)f * K + k) * D;
+    double2* mloc = reinterpret_cast<double2*>(S);  // S is dead now: reuse for the mode vector
+    for (int d = lane; d < D; d += 32) {
+      const double2 v = V[d * D + best];
+      mo[d] = v;
+      mloc[d] = v;
+    }
+    __syncwarp();
+    cw_coef_from_mode(mloc, tab, D, lane, u.coef + ((size_t)f * K + k) * NS);
+    if (lane == 0) {
+      u.concentration[(size_t)f * K + k] = kappa;
+      u.ew[(size_t)f * K + k] = kappa;
+      u.ld[(size_t)f * K + k] = cw_log_norm(kappa, D);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    double wk;
+    if (u.weight_mode == PBB_WEIGHT_CONST) {
+      wk = 1.0 / K;
+    } else {  // saliency branch of estimate_mixture_weight (cwmm.py:129-130 sets saliency = 1)
+      double n1 = 0.0;
+      for (int j = 0; j < K; ++j) n1 += fabs(sumg[j]);
+      wk = sumg[k] / (n1 == 0.0 ? 1e-10 : n1);
+    }
+    u.weight[(size_t)f * K + k] = wk;
+  }
+}
+
+// (mode, concentration, weight) -> E-step form, for CWMM.predict (cwmm.py:26-52)
+struct CwFromModelArgs {
+  int F, D, K;
+  const double2* mode; const double* concentration; const double* weight;  // weight may be null (1/K)
+  double* coef; double* ld; double* ew; double* w;
+};
+
+__global__ void cw_from_model_kernel(const CwFromModelArgs u) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = u.D, K = u.K, NS = D * D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int f = blockIdx.x;
+  int* tab = reinterpret_cast<int*>(smem_raw);
+  for (int s = threadIdx.x; s < NS; s += blockDim.x) tab[s] = slot_pack(D, s);
+  __syncthreads();
+  for (int k = warp; k < K; k += nw) {
+    cw_coef_from_mode(u.mode + ((size_t)f * K + k) * D, tab, D, lane, u.coef + ((size_t)f * K + k) * NS);
+    if (lane == 0) {
+      const double kappa = u.concentration[(size_t)f * K + k];
+      u.ew[(size_t)f * K + k] = kappa;
+      u.ld[(size_t)f * K + k] = cw_log_norm(kappa, D);
+      u.w[(size_t)f * K + k] = u.weight ? u.weight[(size_t)f * K + k] : 1.0 / K;
+    }
   }
 }
 

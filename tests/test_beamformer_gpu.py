@@ -1,0 +1,112 @@
+"""Parity of the device beamforming chain against the reference's golden
+fixtures and its own unit-test known answers.  Eigenvector-type outputs have an
+arbitrary phase and are compared by cos-similarity plus their normalisation
+(tests/test_extraction/test_beamformer.py:18-22 of the reference)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, cos_similarity
+from oracle import pb_bss_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_psd_matches_reference_golden():
+    from pb_bss_b200.extraction import get_power_spectral_density_matrix as psd
+    g = load_golden('beamformer')
+    Y, mask = g['Y'], g['mask']
+    np.testing.assert_allclose(psd(Y, mask), g['psd'], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(psd(Y, mask, normalize=False), g['psd_nonorm'], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(psd(Y, mask[:, 0]), g['psd_single'], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(psd(Y), g['psd_nomask'], rtol=1e-11, atol=1e-14)
+    # (K, F, T) mask with source_dim=-3 -> (K, F, D, D), beamformer.py:156-158
+    out = psd(Y, np.ascontiguousarray(mask.transpose(1, 0, 2)), source_dim=-3)
+    np.testing.assert_allclose(out, g['psd'].transpose(1, 0, 2, 3), rtol=1e-11, atol=1e-14)
+    # complex64 observation
+    np.testing.assert_allclose(psd(Y.astype(np.complex64), mask), g['psd'], rtol=1e-5, atol=1e-6)
+
+
+def test_psd_properties():
+    """Hermitian, PSD, mask-scale invariant (tests/test_extraction/test_covariance_matrix.py:31-107)."""
+    from pb_bss_b200.extraction import get_power_spectral_density_matrix as psd
+    Y = np.swapaxes(synth.noise_stft(7, 130, 8, seed=5), -1, -2).copy()
+    mask = np.random.RandomState(1).uniform(size=(7, 3, 130))
+    P = psd(Y, mask)
+    np.testing.assert_allclose(P, np.conj(np.swapaxes(P, -1, -2)), atol=1e-15)
+    assert np.all(np.linalg.eigvalsh(P) > -1e-12)
+    np.testing.assert_allclose(psd(Y, 7.5 * mask), P, rtol=1e-12)
+    np.testing.assert_allclose(P, O.power_spectral_density(Y, mask), rtol=1e-11, atol=1e-14)
+
+
+def test_vectors_match_reference_golden():
+    from pb_bss_b200 import extraction as E
+    g = load_golden('beamformer')
+    target, noise = g['target'], g['noise']
+    pca = E.get_pca_vector(target)
+    np.testing.assert_allclose(cos_similarity(pca, g['pca']), 1, atol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(pca, axis=-1), 1, atol=1e-12)
+    np.testing.assert_allclose(E.get_mvdr_vector(g['pca'], noise), g['mvdr'], rtol=1e-9, atol=1e-12)
+    gev = E.get_gev_vector(target, noise)
+    np.testing.assert_allclose(cos_similarity(gev, g['gev']), 1, atol=1e-10)
+    np.testing.assert_allclose(np.einsum('fa,fab,fb->f', gev.conj(), noise, gev).real, 1, rtol=1e-10)
+    np.testing.assert_allclose(np.linalg.norm(gev, axis=-1), np.linalg.norm(g['gev'], axis=-1), rtol=1e-9)
+    s, ch = E.get_mvdr_vector_souden(target, noise, return_ref_channel=True)
+    assert ch == int(g['ref_channel'])
+    np.testing.assert_allclose(s, g['souden'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(E.blind_analytic_normalization(g['gev'], noise), g['ban'], rtol=1e-10)
+    np.testing.assert_allclose(E.apply_beamforming_vector(g['gev'], g['Y']), g['applied'], rtol=1e-11, atol=1e-13)
+
+
+def test_gev_equals_pca_for_identity_noise_and_leading_dims():
+    """tests/test_extraction/test_beamformer.py:98-104, shapes :25-118."""
+    from pb_bss_b200 import extraction as E
+    K, F, D = 2, 51, 6
+    target = synth.pos_def_hermitian(K, F, D, D, seed=3)
+    noise = np.broadcast_to(np.eye(D, dtype=np.complex128), (K, F, D, D)).copy()
+    gev = E.get_gev_vector(target, noise)
+    assert gev.shape == (K, F, D)
+    np.testing.assert_allclose(cos_similarity(gev, E.get_pca_vector(target)), 1, atol=1e-10)
+    ref = O.gev_vector(target, synth.pos_def_hermitian(K, F, D, D, seed=4))
+    got = E.get_gev_vector(target, synth.pos_def_hermitian(K, F, D, D, seed=4))
+    np.testing.assert_allclose(cos_similarity(got, ref), 1, atol=1e-9)
+    np.testing.assert_allclose(np.linalg.norm(got, axis=-1), np.linalg.norm(ref, axis=-1), rtol=1e-8)
+    assert E.get_gev_vector(target[0, :1], noise[0, :1]).shape == (1, D)
+
+
+def test_souden_known_answer():
+    """tests/test_extraction/test_beamformer.py:185-209 of the reference."""
+    from pb_bss_b200.extraction import get_mvdr_vector_souden
+    obs = np.array([[0, 0, 1], [0, 0.1, 1], [0.1, 0, 1]])
+    phi_xx = (obs.T.conj() @ obs).astype(np.complex128)
+    w, = get_mvdr_vector_souden(phi_xx[None], np.eye(3, dtype=np.complex128)[None])
+    np.testing.assert_allclose(w, [0.03311258, 0.03311258, 0.99337748], atol=1e-8)
+    w3 = get_mvdr_vector_souden(np.stack([phi_xx] * 3), np.stack([np.eye(3, dtype=np.complex128)] * 3))
+    np.testing.assert_allclose(w3, [w] * 3)
+
+
+def test_error_paths():
+    from pb_bss_b200 import extraction as E
+    D = 4
+    a = synth.pos_def_hermitian(3, D, D, seed=1)
+    b = a.copy()
+    b[1] = -np.eye(D)  # not positive definite
+    with pytest.raises(ValueError):
+        E.get_gev_vector(a, b)
+    sing = a.copy()
+    sing[2] = 0
+    with pytest.raises(np.linalg.LinAlgError):
+        E.get_mvdr_vector(np.ones((3, D), dtype=np.complex128), sing)
+    with pytest.raises(NotImplementedError):
+        E.get_gev_vector(a, a, use_eig=True)
+
+
+def test_mvdr_distortionless_and_broadcast():
+    from pb_bss_b200 import extraction as E
+    F, D = 33, 8
+    noise = synth.pos_def_hermitian(F, D, D, seed=2)
+    atf = np.random.RandomState(0).randn(2, F, D) + 1j * np.random.RandomState(1).randn(2, F, D)
+    w = E.get_mvdr_vector(atf, noise)
+    assert w.shape == (2, F, D)
+    np.testing.assert_allclose(np.einsum('kfd,kfd->kf', w.conj(), atf), 1, atol=1e-10)
+    np.testing.assert_allclose(w, O.mvdr_vector(atf, noise), rtol=1e-9, atol=1e-12)
