@@ -227,6 +227,23 @@ int pbb_blind_analytic_normalization(const void* vector, const void* noise_psd,
 int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
                                  int F, int D, int T, void* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Frequency permutation alignment (pb_bss/permutation_alignment.py).
+ */
+
+/* DHTVPermutationAlignment.calculate_mapping (:295-355), similarity 'cos',
+ * greedy assignment (:525-553).  mask (K, F, T) float64 is only read;
+ * plan: nplan triples (iterations, start, end) as produced by
+ * alignment_plan (:204-293), int32 ON THE DEVICE; features (K, F, T) and
+ * centroid (K, T) are scratch; mapping (K, F) int64 out. */
+int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan,
+                     int nplan, double* features, double* centroid,
+                     long long* mapping, void* stream);
+
+/* apply_mapping (:54-104): out[k, f, :] = mask[mapping[k, f], f, :]. */
+int pbb_apply_mapping(const double* mask, const long long* mapping, int K,
+                      int F, int T, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

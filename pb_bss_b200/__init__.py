@@ -11,5 +11,6 @@ device-memory containers.  There is no CPU fallback.
 from . import _lib  # noqa: F401  (import must not need a GPU)
 from . import distribution  # noqa: F401
 from . import extraction  # noqa: F401
+from . import permutation_alignment  # noqa: F401
 
-__all__ = ['distribution', 'extraction']
+__all__ = ['distribution', 'extraction', 'permutation_alignment']

@@ -1,0 +1,142 @@
+"""Frequency permutation alignment on the device, API of pb_bss/permutation_alignment.py.
+
+``DHTVPermutationAlignment`` (segment-wise centroid matching, :133-355) and
+``apply_mapping`` (:54-104) run in CUDA (``pbb_dhtv_mapping`` /
+``pbb_apply_mapping``); the alignment plan is host logic.
+"""
+import numpy as np
+import torch
+
+from . import _device, _lib
+
+__all__ = ['DHTVPermutationAlignment', 'apply_mapping', 'interleave',
+           'sample_random_mapping']
+
+
+def interleave(*lists):
+    """Round-robin merge of lists of unequal length (:12-39)."""
+    out = []
+    for i in range(max((len(l) for l in lists), default=0)):
+        for l in lists:
+            if i < len(l):
+                out.append(l[i])
+    return iter(out)
+
+
+def sample_random_mapping(K, F, random_state=np.random):
+    """Random mapping (K, F) (:42-51)."""
+    return np.stack([random_state.permutation(K) for _ in range(F)], axis=1)
+
+
+def apply_mapping(mask, mapping):
+    """mask (K, F, ...) , mapping (K, F) -> mask[mapping, range(F)] (:54-104)."""
+    like_numpy = not _device.is_tensor(mask)
+    m = _device.to_device(mask)
+    out_dtype = m.dtype
+    md = m.to(torch.float64)
+    mp = _device.to_device(mapping).to(torch.int64).contiguous()
+    K, F = mp.shape
+    assert K < 20, (K, mp.shape)
+    assert tuple(md.shape[:2]) == (K, F), (md.shape, mp.shape)
+    T = int(np.prod(md.shape[2:])) if md.dim() > 2 else 1
+    md = md.reshape(K, F, T).contiguous()
+    out = _device.empty((K, F, T), torch.float64)
+    lib = _lib.load()
+    _lib.check(lib.pbb_apply_mapping(_device.ptr(md), _device.ptr(mp), K, F, T, _device.ptr(out),
+                                     _device.stream_ptr()), 'pbb_apply_mapping')
+    out = out.reshape(m.shape).to(out_dtype)
+    return _device.to_host(out, like_numpy)
+
+
+class _PermutationAlignment:
+    def calculate_mapping(self, mask, *args, **kwargs):
+        raise NotImplementedError()
+
+    def __call__(self, mask, *args, **kwargs):
+        """mask (K, F, T) -> aligned mask (:116-125)."""
+        mapping = self.calculate_mapping(mask, *args, **kwargs)
+        return self.apply_mapping(mask, mapping)
+
+    @staticmethod
+    def apply_mapping(mask, mapping):
+        return apply_mapping(mask, mapping)
+
+
+class DHTVPermutationAlignment(_PermutationAlignment):
+    """Segment-wise frequency permutation alignment [TranVu2015BSS] (:133-355)."""
+
+    def __init__(self, *, stft_size, segment_start, segment_width,
+                 segment_shift, main_iterations, sub_iterations,
+                 similarity_metric='cos', algorithm='greedy'):
+        self.stft_size = stft_size
+        self.segment_start = segment_start
+        self.segment_width = segment_width
+        self.segment_shift = segment_shift
+        self.main_iterations = main_iterations
+        self.sub_iterations = sub_iterations
+        self.similarity_metric = similarity_metric
+        self.algorithm = algorithm
+        if similarity_metric != 'cos' or algorithm != 'greedy':
+            raise NotImplementedError(
+                "only similarity_metric='cos' with algorithm='greedy' (the "
+                'defaults of the reference) run on the device')
+
+    @classmethod
+    def from_stft_size(cls, stft_size, similarity_metric='cos'):
+        """Presets of the reference (:164-184)."""
+        if stft_size == 512:
+            start = 70
+        elif stft_size == 1024:
+            start = 100
+        else:
+            raise ValueError('There is no default for stft_size={}.', stft_size)
+        return cls(stft_size=stft_size, segment_start=start, segment_width=100,
+                   segment_shift=20, main_iterations=20, sub_iterations=2,
+                   similarity_metric=similarity_metric)
+
+    @property
+    def alignment_plan(self):
+        """List of [iterations, start, end] (:204-293)."""
+        F = self.stft_size // 2 + 1
+        if self.segment_start + self.segment_width > F:
+            raise ValueError(
+                f'segment_start ({self.segment_start}) '
+                f'+ segment_width ({self.segment_width})\n'
+                f'must be smaller than stft_size // 2 + 1 ({F}),\n'
+                f'but it is {self.segment_start + self.segment_width}')
+        lower = [[self.sub_iterations, s, s + self.segment_width]
+                 for s in range(self.segment_start + self.segment_shift,
+                                F - self.segment_width, self.segment_shift)]
+        higher = [[self.sub_iterations, s, s + self.segment_width]
+                  for s in range(self.segment_start - self.segment_shift, 0,
+                                 -self.segment_shift)]
+        first = [self.main_iterations, self.segment_start,
+                 self.segment_start + self.segment_width]
+        if lower:
+            lower[-1][-1] = F
+        else:
+            first[-1] = F
+        if higher:
+            higher[-1][1] = 0
+        else:
+            first[1] = 0
+        return [first] + list(interleave(lower, higher))
+
+    def calculate_mapping(self, mask, plot=False):
+        """mask (K, F, T) -> reverse mapping (K, F) int64 (:295-355)."""
+        like_numpy = not _device.is_tensor(mask)
+        m = _device.to_device(mask).to(torch.float64).contiguous()
+        K, F, T = m.shape
+        assert K < 10, (K, 'Sure?')
+        assert F % 2 == 1, (F, 'Sure? Usually F is odd.')
+        plan = np.asarray(self.alignment_plan, dtype=np.int32)
+        assert plan[:, 2].max() <= F, (plan, F)
+        plan_dev = _device.to_device(np.ascontiguousarray(plan))
+        feat = _device.empty((K, F, T), torch.float64)
+        cent = _device.empty((K, T), torch.float64)
+        mapping = _device.empty((K, F), torch.int64)
+        lib = _lib.load()
+        _lib.check(lib.pbb_dhtv_mapping(_device.ptr(m), K, F, T, _device.ptr(plan_dev), int(plan.shape[0]),
+                                        _device.ptr(feat), _device.ptr(cent), _device.ptr(mapping),
+                                        _device.stream_ptr()), 'pbb_dhtv_mapping')
+        return _device.to_host(mapping, like_numpy)

@@ -1,0 +1,64 @@
+"""DHTV permutation alignment on the device: integer mappings must be EXACTLY
+the reference's (golden fixtures produced by the unmodified reference)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import pb_bss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mapping_matches_reference_golden():
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+    g = load_golden('permutation')
+    for tag, stft in (('a', 512), ('b', 1024)):
+        al = DHTVPermutationAlignment.from_stft_size(stft)
+        assert al.alignment_plan == g[f'{tag}_plan'].tolist()
+        mask = g[f'{tag}_mask']
+        mapping = al.calculate_mapping(mask)
+        assert mapping.dtype == np.int64 and mapping.shape == g[f'{tag}_mapping'].shape
+        np.testing.assert_array_equal(mapping, g[f'{tag}_mapping'])
+        np.testing.assert_array_equal(al.apply_mapping(mask, mapping), g[f'{tag}_aligned'])
+        np.testing.assert_array_equal(al(mask), g[f'{tag}_aligned'])
+    al = DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+                                  main_iterations=5, sub_iterations=2)
+    assert al.alignment_plan == g['c_plan'].tolist()
+    np.testing.assert_array_equal(al.calculate_mapping(g['c_mask']), g['c_mapping'])
+
+
+def test_full_size_alignment_recovers_a_random_permutation():
+    """K=3, F=513, T=500 (BASELINE.json config 3): permute a consistent mask per
+    bin, align, and check against the oracle and the sortedness property
+    (every bin ends up in the same global order)."""
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment, apply_mapping
+    rng = np.random.RandomState(0)
+    K, F, T = 3, 513, 500
+    proto = rng.uniform(size=(K, 1, T)) ** 4
+    mask = proto + 0.3 * rng.uniform(size=(K, F, T))
+    mask /= mask.sum(0, keepdims=True)
+    perm = np.stack([rng.permutation(K) for _ in range(F)], axis=1)
+    permuted = mask[perm, np.arange(F)]
+    al = DHTVPermutationAlignment.from_stft_size(1024)
+    mapping = al.calculate_mapping(permuted)
+    np.testing.assert_array_equal(mapping, O.dhtv_calculate_mapping(permuted, O.dhtv_plan_from_stft_size(1024)))
+    aligned = apply_mapping(permuted, mapping)
+    # up to ONE global permutation the original order is restored
+    order = np.argmax(np.einsum('kft,lft->kl', aligned, mask), axis=1)
+    assert sorted(order.tolist()) == [0, 1, 2]
+    np.testing.assert_array_equal(aligned, mask[order])
+    # permutations: every column of the mapping is a permutation of range(K)
+    assert np.all(np.sort(mapping, axis=0) == np.arange(K)[:, None])
+
+
+def test_apply_mapping_trailing_dims_and_device_tensors():
+    import torch
+    from pb_bss_b200.permutation_alignment import apply_mapping, sample_random_mapping
+    rng = np.random.RandomState(1)
+    K, F = 4, 9
+    mask = rng.uniform(size=(K, F, 5, 3))
+    mapping = sample_random_mapping(K, F, rng)
+    np.testing.assert_array_equal(apply_mapping(mask, mapping), mask[mapping, range(F)])
+    out = apply_mapping(torch.from_numpy(mask).cuda(), torch.from_numpy(mapping).cuda())
+    assert out.is_cuda
+    np.testing.assert_array_equal(out.cpu().numpy(), mask[mapping, range(F)])
