@@ -1,0 +1,118 @@
+"""Multi-GPU execution of the hot path: one process per GPU, bins sharded.
+
+Frequency bins are independent during EM, PSD estimation and beamforming
+(SURVEY.md section 8e), so every rank works on a contiguous slice of bins with
+NO data-path collective.  The only exchange is one all-gather of the per-bin
+affiliations (F, K, T) before the frequency permutation alignment, whose
+centroids couple the bins of a segment (permutation_alignment.py:334); the
+alignment then runs replicated and each rank keeps its slice of the result.
+
+``torch.distributed`` is only the transport (NCCL over NVLink on the GPUs; the
+same code runs over gloo on CPU tensors, which is how the host logic is
+tested).  Without an initialised process group everything degrades to a
+single rank.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ['world', 'bin_shards', 'local_bins', 'all_gather_bins',
+           'sharded_separation']
+
+
+def world(group=None):
+    """(rank, world_size) of the process group, (0, 1) if there is none."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def bin_shards(F, world_size):
+    """Contiguous, balanced bin ranges: [(lo, hi)] * world_size (sizes differ by
+    at most one; F=513 over 8 ranks -> 65, 64, ..., 64)."""
+    base, extra = divmod(F, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def local_bins(F, group=None):
+    rank, ws = world(group)
+    return bin_shards(F, ws)[rank]
+
+
+def all_gather_bins(local, F, group=None):
+    """local (F_rank, ...) on every rank -> (F, ...) on every rank.
+
+    Slices are padded to the largest shard so a single
+    ``all_gather_into_tensor`` moves everything (3 MB of float32-equivalent
+    affiliations at F=513, K=3, T=500: latency bound over NVLink)."""
+    rank, ws = world(group)
+    if ws == 1:
+        assert local.shape[0] == F, (local.shape, F)
+        return local
+    shards = bin_shards(F, ws)
+    nmax = max(hi - lo for lo, hi in shards)
+    lo, hi = shards[rank]
+    assert local.shape[0] == hi - lo, (local.shape, shards[rank])
+    pad = torch.zeros((nmax, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:hi - lo] = local
+    out = torch.empty((ws * nmax, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    out = out.reshape(ws, nmax, *local.shape[1:])
+    return torch.cat([out[r, :h - l] for r, (l, h) in enumerate(shards)], dim=0)
+
+
+def sharded_separation(y_local, initialization_local, F, *, iterations=100,
+                       stft_size=None, beamformer='gev', group=None,
+                       trainer_kwargs=None):
+    """BASELINE.json config 3 on this rank's bin slice.
+
+    cACGMM fit + predict on the local bins -> all-gather of the affiliations
+    -> DHTV permutation alignment (replicated) -> local masks -> local PSDs ->
+    local GEV (or MVDR on the PCA steering vector) beamforming vectors ->
+    enhanced local STFT.
+
+    y_local: (F_rank, T, D) CUDA tensor (this rank's bins of the utterance);
+    initialization_local: (F_rank, K, T).  Returns a dict with the local
+    ``model``, ``affiliation`` (aligned, (F_rank, K, T)), the global
+    ``mapping`` (K, F), ``vectors`` (F_rank, K, D) and ``enhanced``
+    (F_rank, K, T).
+    """
+    from .distribution import CACGMMTrainer
+    from .extraction import (apply_beamforming_vector, get_gev_vector,
+                             get_mvdr_vector, get_pca_vector,
+                             get_power_spectral_density_matrix)
+    from .permutation_alignment import DHTVPermutationAlignment, apply_mapping
+    rank, ws = world(group)
+    lo, hi = bin_shards(F, ws)[rank]
+    assert y_local.shape[0] == hi - lo, (y_local.shape, (lo, hi))
+    model = CACGMMTrainer().fit(y_local, initialization=initialization_local,
+                                iterations=iterations, **(trainer_kwargs or {}))
+    aff_local = model.predict(y_local)                       # (F_rank, K, T)
+    aff = all_gather_bins(aff_local, F, group)               # the one collective
+    if stft_size is None:
+        stft_size = 2 * (F - 1)
+    aligner = DHTVPermutationAlignment.from_stft_size(stft_size)
+    mask_kft = aff.permute(1, 0, 2).contiguous()             # (K, F, T)
+    mapping = aligner.calculate_mapping(mask_kft)            # replicated, identical on all ranks
+    aligned = apply_mapping(mask_kft[:, lo:hi].contiguous(), mapping[:, lo:hi].contiguous())
+    aligned = aligned.permute(1, 0, 2).contiguous()          # (F_rank, K, T)
+    Y = y_local.transpose(-1, -2).contiguous()               # (F_rank, D, T)
+    psd = get_power_spectral_density_matrix(Y, aligned)      # (F_rank, K, D, D)
+    K = psd.shape[1]
+    total = psd.sum(1, keepdim=True)
+    noise = (total - psd).contiguous()                       # interference + noise per target class
+    if beamformer == 'gev':
+        vectors = get_gev_vector(psd, noise)                 # (F_rank, K, D)
+    elif beamformer == 'mvdr':
+        vectors = get_mvdr_vector(get_pca_vector(psd).permute(1, 0, 2), noise.permute(1, 0, 2, 3).contiguous()
+                                  ).permute(1, 0, 2)
+    else:
+        raise ValueError(beamformer)
+    enhanced = apply_beamforming_vector(vectors.permute(1, 0, 2).contiguous(), Y.unsqueeze(0).expand(K, *Y.shape))
+    return dict(model=model, affiliation=aligned, mapping=mapping,
+                vectors=vectors, enhanced=enhanced.permute(1, 0, 2))
