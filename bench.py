@@ -57,41 +57,54 @@ def _inputs(rank):
 # clocks sampler (nvidia-smi in a background thread during the timed region)
 # --------------------------------------------------------------------------
 class ClockSampler:
+    """Streams `nvidia-smi -lms 50` for one GPU while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_power_cap,power.draw')
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                     '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '50'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # first sample is on its way before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        self.rows = [[c.strip() for c in line.split(',')] for line in out.strip().splitlines() if line.strip()]
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        rows = [r for r in self.rows if len(r) >= 6 and num(r[0]) is not None]
+        sm = [num(r[0]) for r in rows]
+        mx = [num(r[1]) for r in rows if num(r[1]) is not None]
+        # "under load": samples within 25% of the highest clock seen (idle samples bracket the region)
+        load = [v for v in sm if v >= 0.75 * max(sm)] if sm else []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
-                          for i in range(4) if r[2 + i].lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None,
-                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith('active')})
+        pw = [num(r[6]) for r in rows if len(r) > 6 and num(r[6]) is not None]
+        return {'sm_mhz': float(np.median(load)) if load else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm), 'power_w_max': max(pw) if pw else None}
 
 
 # --------------------------------------------------------------------------
@@ -254,11 +267,18 @@ def b200_arm(args):
     # F*T*D*16 + 2*F*K*(D*D*16 + D*8 + 8)
     b_iter = F * T * D * 16 + 2 * F * K * (D * D * 16 + D * 8 + 8)
     roofline = None
+    traffic = None
+    try:  # DRAM bytes of the same kernel + workload from the committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'em_kernel_metrics.json')))['traffic_bytes_per_launch']
+    except Exception:
+        pass
     if prof and prof['ms_total'] > 0:
         iters_covered = ITERS  # the dominant kernel(s) of one fit cover all EM iterations
         achieved = b_iter * iters_covered / (prof['ms_total'] * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                    'traffic_source': 'profiles/em_kernel_metrics.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch = 100 EM iterations)',
+                    'algorithmic_bytes_per_launch': b_iter * iters_covered,
                     'kernel': prof['kernel'], 'kernel_launches_per_fit': prof['launches'],
                     'kernel_ms_per_fit': prof['ms_total'],
                     'algorithmic_bytes_per_em_iteration': b_iter,
@@ -288,7 +308,7 @@ def b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
