@@ -234,8 +234,11 @@ int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
 /* DHTVPermutationAlignment.calculate_mapping (:295-355), similarity 'cos',
  * greedy assignment (:525-553).  mask (K, F, T) float64 is only read;
  * plan: nplan triples (iterations, start, end) as produced by
- * alignment_plan (:204-293), int32 ON THE DEVICE; features (K, F, T) and
- * centroid (K, T) are scratch; mapping (K, F) int64 out. */
+ * alignment_plan (:204-293) -- a small HOST array (it drives the launch
+ * sequence); features (K, F, T) and centroid
+ * (pbb_dhtv_scratch_doubles doubles) are device scratch; mapping (K, F) int64 out.
+ * The reference's early exit is reproduced with device-side flags. */
+size_t pbb_dhtv_scratch_doubles(int K, int T, const int* plan, int nplan);
 int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan,
                      int nplan, double* features, double* centroid,
                      long long* mapping, void* stream);

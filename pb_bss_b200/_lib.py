@@ -61,7 +61,8 @@ SIGNATURES = {
     'pbb_mvdr': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     'pbb_souden': (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     'pbb_blind_analytic_normalization': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    'pbb_dhtv_mapping': (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    'pbb_dhtv_scratch_doubles': (_sz, [_i, _i, ctypes.POINTER(_i), _i]),
+    'pbb_dhtv_mapping': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     'pbb_apply_mapping': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     'pbb_apply_beamforming_vector': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }

@@ -34,84 +34,103 @@ __global__ void dhtv_normalize_kernel(const double* __restrict__ mask, double* _
   for (int t = threadIdx.x; t < T; t += blockDim.x) feat[(size_t)row * T + t] = m[t] / d;
 }
 
-// The whole alignment plan in one single-CTA kernel: the work per iteration is a
-// few hundred kflop, the algorithm is a chain of ~60 dependent iterations, so
-// latency (block barriers, L2 round trips) is what matters, not parallel width.
-__global__ void __launch_bounds__(kDhtvThreads) dhtv_kernel(double* __restrict__ feat, double* __restrict__ cent,
-                                                            const int* __restrict__ plan, int nplan, int K, int F,
-                                                            int T, long long* __restrict__ mapping) {
-  __shared__ double red[32];
+// One alignment iteration = two launches (centroid partial sums over bin slices, then one
+// warp per bin: scores, greedy assignment, permutation).  Every launch of the fixed plan is
+// issued up front; the reference's early exit ("nothing changed", :352-353) is a device-side
+// flag: iteration i of a segment returns immediately unless iteration i-1 changed something.
+constexpr int kDhtvSlices = 8;   // bin slices of the centroid sum (summed in fixed order)
+
+__global__ void dhtv_init_mapping_kernel(long long* __restrict__ mapping, int K, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * F) mapping[i] = i / F;
+}
+
+// partial[slice][k][t] = sum over the slice's bins of features[k][f][t]
+__global__ void dhtv_centroid_kernel(const double* __restrict__ feat, double* __restrict__ partial,
+                                     const int* __restrict__ prev_changed, int K, int F, int T, int start, int end) {
+  if (prev_changed != nullptr && *prev_changed == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * T) return;
+  const int k = i / T, t = i - k * T;
+  const int n = end - start, per = (n + kDhtvSlices - 1) / kDhtvSlices;
+  const int f0 = start + blockIdx.y * per, f1 = min(end, f0 + per);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int f = f0;
+  for (; f + 3 < f1; f += 4) {
+    s0 += feat[((size_t)k * F + f) * T + t];
+    s1 += feat[((size_t)k * F + f + 1) * T + t];
+    s2 += feat[((size_t)k * F + f + 2) * T + t];
+    s3 += feat[((size_t)k * F + f + 3) * T + t];
+  }
+  for (; f < f1; ++f) s0 += feat[((size_t)k * F + f) * T + t];
+  partial[(size_t)blockIdx.y * K * T + i] = (s0 + s1) + (s2 + s3);
+}
+
+// one CTA = 4 warps = 4 bins of the segment
+__global__ void __launch_bounds__(128) dhtv_assign_kernel(double* __restrict__ feat, const double* __restrict__ partial,
+                                                          const int* __restrict__ prev_changed,
+                                                          int* __restrict__ changed, int K, int F, int T, int start,
+                                                          int end, long long* __restrict__ mapping) {
+  if (prev_changed != nullptr && *prev_changed == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* cent = reinterpret_cast<double*>(smem_raw);  // [K][T]
+  __shared__ double red[4];
   __shared__ double cnorm[kDhtvMaxK];
-  __shared__ int changed;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  for (int i = tid; i < K * F; i += blockDim.x) mapping[i] = i / F;  // mapping[k][f] = k
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // centroid = mean over the segment's bins, then L2-normalised over time (:334-340)
+  const double inv_n = 1.0 / (double)(end - start);
+  for (int i = tid; i < K * T; i += blockDim.x) {
+    double s = 0.0;
+    for (int sl = 0; sl < kDhtvSlices; ++sl) s += partial[(size_t)sl * K * T + i];
+    cent[i] = s * inv_n;
+  }
   __syncthreads();
-  for (int p = 0; p < nplan; ++p) {
-    const int iters = plan[3 * p], start = plan[3 * p + 1], end = plan[3 * p + 2];
-    for (int it = 0; it < iters; ++it) {
-      // (a) centroid over the segment's bins, L2-normalised over time (:334-340)
-      for (int i = tid; i < K * T; i += blockDim.x) {
-        const int k = i / T, t = i - k * T;
-        double s = 0.0;
-        for (int f = start; f < end; ++f) s += feat[((size_t)k * F + f) * T + t];
-        cent[i] = s / (double)(end - start);
-      }
-      if (tid == 0) changed = 0;
-      __syncthreads();
-      for (int k = 0; k < K; ++k) {
-        double s = 0.0;
-        for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
-        const double n = sqrt(block_sum(s, red));
-        if (tid == 0) cnorm[k] = fmax(n, kTiny);
-      }
-      __syncthreads();
-      for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
-      __syncthreads();
-      // (b) one warp per bin: K x K scores, greedy assignment, permute (:342-350)
-      for (int f = start + warp; f < end; f += nwarp) {
-        double score[kDhtvMaxK * kDhtvMaxK];
-        for (int kr = 0; kr < K; ++kr)
-          for (int km = 0; km < K; ++km) {
-            double s = 0.0;
-            for (int t = lane; t < T; t += 32) s += feat[((size_t)km * F + f) * T + t] * cent[kr * T + t];
-            score[kr * K + km] = warp_sum(s);  // identical in every lane
-          }
-        int perm[kDhtvMaxK];
-        bool ident = true;
-        for (int r = 0; r < K; ++r) {
-          // first maximum of the row-major flattened matrix (np.argmax), then blank its row and column
-          int bi = 0, bj = 0;
-          double best = -INFINITY;
-          bool found = false;
-          for (int i = 0; i < K; ++i)
-            for (int j = 0; j < K; ++j) {
-              const double v = score[i * K + j];
-              if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
-            }
-          for (int j = 0; j < K; ++j) score[bi * K + j] = -INFINITY;
-          for (int i = 0; i < K; ++i) score[i * K + bj] = -INFINITY;
-          perm[bi] = bj;
-        }
-        for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
-        if (!ident) {
-          for (int t = lane; t < T; t += 32) {
-            double v[kDhtvMaxK];
-            for (int k = 0; k < K; ++k) v[k] = feat[((size_t)k * F + f) * T + t];
-            for (int k = 0; k < K; ++k) feat[((size_t)k * F + f) * T + t] = v[perm[k]];
-          }
-          if (lane == 0) {
-            long long mv[kDhtvMaxK];
-            for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
-            for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
-            changed = 1;
-          }
-        }
-      }
-      __syncthreads();
-      const int ch = changed;
-      __syncthreads();
-      if (!ch) break;  // nothing_changed (:352-353)
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+    for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
+    const double n = sqrt(block_sum(s, red));
+    if (tid == 0) cnorm[k] = fmax(n, kTiny);
+  }
+  __syncthreads();
+  for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
+  __syncthreads();
+  const int f = start + blockIdx.x * 4 + warp;
+  if (f >= end) return;
+  double score[kDhtvMaxK * kDhtvMaxK];
+  for (int kr = 0; kr < K; ++kr)
+    for (int km = 0; km < K; ++km) {
+      double s = 0.0;
+      for (int t = lane; t < T; t += 32) s += feat[((size_t)km * F + f) * T + t] * cent[kr * T + t];
+      score[kr * K + km] = warp_sum(s);  // identical in every lane
     }
+  int perm[kDhtvMaxK];
+  for (int r = 0; r < K; ++r) {
+    // first maximum of the row-major flattened matrix (np.argmax), then blank its row and column (:525-553)
+    int bi = 0, bj = 0;
+    double best = -INFINITY;
+    bool found = false;
+    for (int i = 0; i < K; ++i)
+      for (int j = 0; j < K; ++j) {
+        const double v = score[i * K + j];
+        if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
+      }
+    for (int j = 0; j < K; ++j) score[bi * K + j] = -INFINITY;
+    for (int i = 0; i < K; ++i) score[i * K + bj] = -INFINITY;
+    perm[bi] = bj;
+  }
+  bool ident = true;
+  for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
+  if (ident) return;
+  for (int t = lane; t < T; t += 32) {
+    double v[kDhtvMaxK];
+    for (int k = 0; k < K; ++k) v[k] = feat[((size_t)k * F + f) * T + t];
+    for (int k = 0; k < K; ++k) feat[((size_t)k * F + f) * T + t] = v[perm[k]];
+  }
+  if (lane == 0) {
+    long long mv[kDhtvMaxK];
+    for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
+    for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
+    *changed = 1;
   }
 }
 
@@ -137,19 +156,49 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
   PBB_CHECK_ARG(K > 0 && K <= kDhtvMaxK, 2, "need 0 < K < 10 (permutation_alignment.py:200)");
   PBB_CHECK_ARG(F > 0, 3, "F must be positive");
   PBB_CHECK_ARG(T > 0, 4, "T must be positive");
-  PBB_CHECK_ARG(plan != nullptr && nplan > 0, 5, "alignment plan is empty");
-  PBB_CHECK_ARG(features && centroid, 7, "scratch (features (K,F,T), centroid (K,T)) is null");
+  PBB_CHECK_ARG(plan != nullptr && nplan > 0 && nplan <= 4096, 5, "alignment plan: HOST array of (iterations, start, end)");
+  PBB_CHECK_ARG(features && centroid, 7, "scratch is null (pbb_dhtv_scratch_doubles)");
   PBB_CHECK_ARG(mapping != nullptr, 9, "mapping is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int total_iters = 0;
+  for (int p = 0; p < nplan; ++p) {
+    PBB_CHECK_ARG(plan[3 * p] >= 0 && plan[3 * p + 1] >= 0 && plan[3 * p + 2] <= F && plan[3 * p + 1] < plan[3 * p + 2],
+                  5, "alignment plan entry out of range");
+    total_iters += plan[3 * p];
+  }
+  // centroid scratch: kDhtvSlices * K * T doubles of partial sums, then the int "changed" flags
+  double* partial = centroid;
+  int* changed = reinterpret_cast<int*>(centroid + (size_t)kDhtvSlices * K * T);
+  PBB_CUDA(cudaMemsetAsync(changed, 0, (size_t)(total_iters + 1) * sizeof(int), st));
+  PBB_CHECK_ARG((size_t)K * T * sizeof(double) <= 200 * 1024, 4, "K * T too large for the shared-memory centroid");
+  PBB_CUDA(cudaFuncSetAttribute(dhtv_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   {
     LaunchScope ls("dhtv_normalize_kernel", st);
     dhtv_normalize_kernel<<<K * F, 128, 0, st>>>(mask, features, K * F, T);
+    dhtv_init_mapping_kernel<<<(K * F + 255) / 256, 256, 0, st>>>(mapping, K, F);
     PBB_CUDA(cudaGetLastError());
   }
-  LaunchScope ls("dhtv_kernel", st);
-  dhtv_kernel<<<1, kDhtvThreads, 0, st>>>(features, centroid, plan, nplan, K, F, T, mapping);
+  LaunchScope ls("dhtv_iterations", st);
+  int idx = 0;
+  for (int p = 0; p < nplan; ++p) {
+    const int iters = plan[3 * p], start = plan[3 * p + 1], end = plan[3 * p + 2];
+    for (int it = 0; it < iters; ++it, ++idx) {
+      const int* prev = it == 0 ? nullptr : changed + idx - 1;
+      dhtv_centroid_kernel<<<dim3((K * T + 127) / 128, kDhtvSlices), 128, 0, st>>>(features, partial, prev, K, F, T,
+                                                                                   start, end);
+      dhtv_assign_kernel<<<(end - start + 3) / 4, 128, (size_t)K * T * sizeof(double), st>>>(
+          features, partial, prev, changed + idx, K, F, T, start, end, mapping);
+    }
+  }
   PBB_CUDA(cudaGetLastError());
   return 0;
+}
+
+// doubles of `centroid` scratch pbb_dhtv_mapping needs
+size_t pbb_dhtv_scratch_doubles(int K, int T, const int* plan, int nplan) {
+  size_t iters = 0;
+  for (int p = 0; p < nplan; ++p) iters += (size_t)plan[3 * p];
+  return (size_t)kDhtvSlices * K * T + (iters + 2) / 2 + 2;
 }
 
 int pbb_apply_mapping(const double* mask, const long long* mapping, int K, int F, int T, double* out,

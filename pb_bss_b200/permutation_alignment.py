@@ -4,6 +4,8 @@
 ``apply_mapping`` (:54-104) run in CUDA (``pbb_dhtv_mapping`` /
 ``pbb_apply_mapping``); the alignment plan is host logic.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -131,12 +133,13 @@ class DHTVPermutationAlignment(_PermutationAlignment):
         assert F % 2 == 1, (F, 'Sure? Usually F is odd.')
         plan = np.asarray(self.alignment_plan, dtype=np.int32)
         assert plan[:, 2].max() <= F, (plan, F)
-        plan_dev = _device.to_device(np.ascontiguousarray(plan))
-        feat = _device.empty((K, F, T), torch.float64)
-        cent = _device.empty((K, T), torch.float64)
-        mapping = _device.empty((K, F), torch.int64)
+        plan = np.ascontiguousarray(plan)
+        plan_p = plan.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
         lib = _lib.load()
-        _lib.check(lib.pbb_dhtv_mapping(_device.ptr(m), K, F, T, _device.ptr(plan_dev), int(plan.shape[0]),
+        feat = _device.empty((K, F, T), torch.float64)
+        cent = _device.empty((int(lib.pbb_dhtv_scratch_doubles(K, T, plan_p, int(plan.shape[0]))),), torch.float64)
+        mapping = _device.empty((K, F), torch.int64)
+        _lib.check(lib.pbb_dhtv_mapping(_device.ptr(m), K, F, T, plan_p, int(plan.shape[0]),
                                         _device.ptr(feat), _device.ptr(cent), _device.ptr(mapping),
                                         _device.stream_ptr()), 'pbb_dhtv_mapping')
         return _device.to_host(mapping, like_numpy)
