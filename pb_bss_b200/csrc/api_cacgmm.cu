@@ -4,18 +4,8 @@
 
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
-#include "em_quad.cuh"
 #include "prof.cuh"
 
-#ifndef PBB_QUAD_FPL
-#define PBB_QUAD_FPL 1
-#endif
-#ifndef PBB_QUAD_CREG
-#define PBB_QUAD_CREG false
-#endif
-#ifndef PBB_LEAN_KERNEL
-#define PBB_LEAN_KERNEL 0  // 0: slot-group-per-warp kernel (em_persistent.cuh), 1: quad-lane kernel (em_quad.cuh)
-#endif
 #ifndef PBB_CTA_FPL
 #define PBB_CTA_FPL 2
 #endif
@@ -71,13 +61,16 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n); return o; };
   const int zs = (T + 31) / 32 * 32;
-  const size_t o_z = take((size_t)F * D * zs * sizeof(double2));
+  const size_t nchunks = ((size_t)zs + kStageFrames - 1) / kStageFrames;
+  const size_t z_plain = (size_t)F * D * zs * sizeof(double2);
+  const size_t z_staged = (size_t)F * nchunks * stage_rows(D % 2 == 0 ? D : D + 1) * kStageFrames * sizeof(double2);
+  const size_t o_z = take(z_plain > z_staged ? z_plain : z_staged);
   const size_t o_flags = take((size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8);
   const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
   const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
-  const size_t o_ld = take((size_t)F * K * sizeof(double));
+  const size_t o_ld = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
   const size_t o_w = take((size_t)F * K * sizeof(double));
-  const size_t o_ew = take((size_t)F * K * sizeof(double));
+  const size_t o_ew = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
   const size_t o_ll = take((size_t)F * max_chunks(T) * sizeof(double));
   char* b = reinterpret_cast<char*>(base);
   ws.z = b + o_z;
@@ -104,6 +97,19 @@ static int launch_normalize(const void* y, void* z, int F, int T, int D, int swa
   LaunchScope ls("normalize_kernel", st);
   normalize_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T,
                                                     D, swap, zs);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename CT>
+static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, cudaStream_t st) {
+  const int block = 64;  // divides kStageFrames
+  const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
+  dim3 grid(nchunks * (kStageFrames / block), F);
+  const size_t smem = (size_t)block * (D + 1) * sizeof(double2);
+  LaunchScope ls("normalize_staged_kernel", st);
+  normalize_staged_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T, D,
+                                                          stage_rows(D), kStageFrames, nchunks);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -221,22 +227,15 @@ static int launch_persistent_generic(Kern kern, int threads, size_t smem, int* c
   return 0;
 }
 
-// full = saliency / activity mask / log-domain softmax: slot-group-per-warp kernel (em_persistent.cuh);
-// lean = quad-lane kernel (em_quad.cuh), two frames per lane
+// full = saliency / activity mask / log-domain softmax; lean = product-form softmax, 2 frames per lane
 template <int D, int K, typename CT>
 static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
   static int cache_full = 0, cache_lean = 0;
   if (full)
     return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, 32 * (D / 2),
                                      sizeof(PersistSmem<D, K, CT>), &cache_full, a, "em_persistent_kernel", st);
-#if PBB_LEAN_KERNEL == 1
-  constexpr int FPL = PBB_QUAD_FPL;
-  return launch_persistent_generic(em_quad_kernel<D, K, CT, FPL, PBB_QUAD_CREG>, 32 * kQuadWarps, sizeof(QuadSmem<D, K, CT>),
-                                   &cache_lean, a, "em_quad_kernel", st);
-#else
   return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL>, 32 * (D / 2),
                                    sizeof(PersistSmem<D, K, CT>), &cache_lean, a, "em_persistent_kernel", st);
-#endif
 }
 
 template <int D, int K>
@@ -331,8 +330,14 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
-                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
+  const bool persistent = fast_shape(D, K) && !(opt->reserved & 1);
+  int r;
+  if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, st);
+  else
+    r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                          : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
   if (r) return r;
 
   EmArgs a;
@@ -356,7 +361,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   u.status = status;
 
   const bool fast_sm = softmax_fast_ok(D, opt);
-  if (fast_shape(D, K) && !(opt->reserved & 1)) {
+  if (persistent) {
     // ---- persistent path: every EM iteration in one launch (em_persistent.cuh) ----
     PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
     if (init_aff == nullptr) {
@@ -390,9 +395,9 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
       cudaStreamSynchronize(st);
       cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
       unsigned long long tot = 0;
-      for (int i = 0; i < 7; ++i) tot += ph[i];
-      static const char* nm[7] = {"ticket+flag", "stage/chunk-barrier", "tma-wait", "em-steps", "reduce", "update", "publish"};
-      for (int i = 0; i < 7; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%\n", nm[i], 100.0 * ph[i] / (double)tot);
+      for (int i = 0; i < 8; ++i) tot += ph[i];
+      static const char* nm[8] = {"ticket+flag", "chunk-top", "tma-wait", "em-steps", "reduce", "update", "publish", "task-start"};
+      for (int i = 0; i < 8; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%\n", nm[i], 100.0 * ph[i] / (double)tot);
     }
 #endif
     u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model

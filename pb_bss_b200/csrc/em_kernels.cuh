@@ -884,4 +884,48 @@ __global__ void normalize_kernel(const CT* __restrict__ y, CT* __restrict__ z, i
   }
 }
 
+// Normalisation into the staged layout of the persistent kernel:
+// out[f][c][r][i] = z[f][row_channel(D, r)][c * SF + i]  (zero for frames >= T), so that one ring
+// stage (ROWS rows x SF frames) is one contiguous block.  One CTA per (frame tile, bin).
+template <typename CT>
+__global__ void normalize_staged_kernel(const CT* __restrict__ y, CT* __restrict__ z, int F, int T, int D, int rows,
+                                        int SF, int nchunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);  // [blockDim.x][D + 1]
+  const int f = blockIdx.y;
+  const int t0 = blockIdx.x * blockDim.x;                // blockDim.x divides SF
+  const int nt = max(0, min((int)blockDim.x, T - t0));
+  const int ldt = D + 1;
+  const CT* __restrict__ yf = y + ((size_t)f * T + t0) * D;
+  for (int i = threadIdx.x; i < nt * D; i += blockDim.x) {
+    const int tt = i / D, d = i - tt * D;
+    tile[tt * ldt + d] = ld_cplx(yf + i);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nt) {
+    double n2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double2 v = tile[threadIdx.x * ldt + d];
+      n2 += v.x * v.x + v.y * v.y;
+    }
+    double nrm = sqrt(n2);
+    if (nrm == 0.0) nrm = kTiny;
+    nrm = fmax(nrm, kTiny);
+    for (int d = 0; d < D; ++d) {
+      double2 v = tile[threadIdx.x * ldt + d];
+      v.x = v.x / nrm; v.y = v.y / nrm;
+      tile[threadIdx.x * ldt + d] = v;
+    }
+  }
+  __syncthreads();
+  const int c = t0 / SF, i0 = t0 - c * SF;
+  CT* __restrict__ zc = z + ((size_t)f * nchunks + c) * rows * SF;
+  for (int i = threadIdx.x; i < rows * (int)blockDim.x; i += blockDim.x) {
+    const int r = i / blockDim.x, tt = i - r * blockDim.x;
+    double2 v = make_double2(0.0, 0.0);
+    if (tt < nt) v = tile[tt * ldt + row_channel(D, r)];
+    st_cplx(zc + (size_t)r * SF + i0 + tt, v.x, v.y);
+  }
+}
+
 }  // namespace pbb

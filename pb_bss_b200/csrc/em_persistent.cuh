@@ -42,8 +42,9 @@ namespace pbb {
 #endif
 
 struct PersistArgs {
-  const void* z;   // (F, D, zs) unit-norm observation, rows zero padded to zs
-  int zs;          // row stride in frames, multiple of 32
+  const void* z;   // staged layout (F, nchunks, ROWS, kStageFrames): every ring stage is one
+                   // contiguous block (channels + repeated rows, zero padded), see normalize_staged_kernel
+  int zs;          // padded frame count, multiple of 32
   int F, T;
   int iterations;  // EM iterations in this launch
   int first_is_m;  // iteration 0 is an M-step from aff_in with q = 1 (cacgmm.py:206-228)
@@ -135,15 +136,18 @@ struct PersistSmem {
   CT zbuf[kStages][ROWS][kStageFrames];
   double2 A[K][NS];     // scatter matrix / its inverse
   double2 V[K][NS];     // eigenvectors (Jacobi fallback only)
-  double coef[K][NS];   // E-step form of the bin's model
+  double coef[2][K][NS];  // E-step form of the bin's model (double buffered: next task's model is prefetched)
   double xq[2][M][2 * K][32];  // partial quadratic forms, up to 2 frames per lane
   double S[K][NS + 1];  // scatter sums + sum of gamma
   double rot[K][((D + 1) / 2) * 6];
   double lam[K][D];
-  double ld[K], w[K], ew[K];
+  double ld[K], w[K];
+  alignas(16) double ew[2][4];  // w_k exp(ld_min - ld_k) of the current / prefetched model
+  alignas(16) double raw[2][8];  // lean variant: published (sum gamma_k, ld_k), padded to 4 + 4, cp.async target
   uint64_t full[kStages];
   int tab[NS];
   int tick[2];
+  int ready;              // the next task's model was already published when probed
 };
 
 template <int D>
@@ -233,13 +237,13 @@ __device__ __forceinline__ void softmax_product(double (&q)[K], const double* __
 // No per-frame masking: padded frames have z = 0, add nothing to the scatter
 // sums, and their gamma is subtracted analytically by the caller.
 template <int D, int K, typename CT>
-__device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int g, int st, int nsteps, int lane, int& buf,
-                                           double eps, double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K],
-                                           int j0 = 0) {
+__device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps, int lane,
+                                           int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
+                                           double (&sg)[K], int j0 = 0) {
   using G = GroupDims<D>;
   constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
   const CT* __restrict__ zrow = &sm.zbuf[st][2 * g][0] + lane + 32 * j0;
-  const double* __restrict__ cg = &sm.coef[0][g * NSG];
+  const double* __restrict__ cg = &sm.coef[cb][0][g * NSG];
 #pragma unroll 1
   for (int j = 0; j < nsteps; ++j, zrow += 32) {
     double2 x[NLOC];
@@ -275,7 +279,7 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int g, int
     }
     buf ^= 1;
     double gam[K], cw[K];
-    softmax_product<D, K>(q, sm.ew, eps, gam, cw);
+    softmax_product<D, K>(q, sm.ew[cb], eps, gam, cw);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       sg[k] += gam[k];
@@ -290,13 +294,13 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int g, int
 // frames, and their E-step / softmax dependency chains interleave, which is what
 // keeps the fp64 pipe busy with only two warps per scheduler.
 template <int D, int K, typename CT>
-__device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int g, int st, int nsteps2, int lane,
+__device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps2, int lane,
                                             int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
                                             double (&sg)[K]) {
   using G = GroupDims<D>;
   constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
   const CT* __restrict__ zrow = &sm.zbuf[st][2 * g][0] + lane;
-  const double* __restrict__ cg = &sm.coef[0][g * NSG];
+  const double* __restrict__ cg = &sm.coef[cb][0][g * NSG];
 #pragma unroll 1
   for (int j = 0; j < nsteps2; ++j, zrow += 64) {
     double psiA[NSG], psiB[NSG];
@@ -345,8 +349,8 @@ __device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int g, in
     }
     buf ^= 1;
     double gA[K], cA[K], gB[K], cB[K];
-    softmax_product<D, K>(qA, sm.ew, eps, gA, cA);
-    softmax_product<D, K>(qB, sm.ew, eps, gB, cB);
+    softmax_product<D, K>(qA, sm.ew[cb], eps, gA, cA);
+    softmax_product<D, K>(qB, sm.ew[cb], eps, gB, cB);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       sg[k] += gA[k] + gB[k];
@@ -424,7 +428,7 @@ __device__ __forceinline__ void general_chunk(const PersistArgs& a, PersistSmem<
     bool done = false;
     if constexpr (FULL) {
       if (!mstep_only) {
-        const double* __restrict__ cg = &sm.coef[0][g * NSG];
+        const double* __restrict__ cg = &sm.coef[0][0][g * NSG];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           double pq = 0.0;
@@ -448,12 +452,12 @@ __device__ __forceinline__ void general_chunk(const PersistArgs& a, PersistSmem<
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             const bool on = a.activity[((size_t)bin * K + k) * T + tc] != 0;
-            ewm[k] = on ? sm.ew[k] : 0.0;
+            ewm[k] = on ? sm.ew[0][k] : 0.0;
             wm[k] = on ? sm.w[k] : 0.0;
           }
           softmax_general<D, K>(q, sm.ld, wm, ewm, fast, a.aff_eps, gam, invq);
         } else {
-          softmax_general<D, K>(q, sm.ld, sm.w, sm.ew, fast, a.aff_eps, gam, invq);
+          softmax_general<D, K>(q, sm.ld, sm.w, sm.ew[0], fast, a.aff_eps, gam, invq);
         }
         done = true;
       }
@@ -552,41 +556,61 @@ em_persistent_kernel(const PersistArgs a) {
   int cur = sm.tick[0];
   unsigned chunk_cnt = 0;  // chunks consumed so far by this CTA (ring position)
 
-  auto issue_chunk = [&](int bin, int c, unsigned n) {  // warp 0: lane r copies staged row r
-    const int st = n & 1u;
-    const int t0 = c * kStageFrames;
-    const int nf = min(kStageFrames, zs - t0);
-    const uint32_t bytes = (uint32_t)nf * sizeof(CT);
-    if (lane == 0) mbar_expect_tx(&sm.full[st], bytes * SM::ROWS);
-    if (lane < SM::ROWS)
-      bulk_g2s(&sm.zbuf[st][lane][0], zbase + ((size_t)bin * D + row_channel(D, lane)) * zs + t0, bytes,
+  // One 1-D TMA bulk copy per ring stage: the staged layout keeps the ROWS x kStageFrames block
+  // of a (bin, chunk) contiguous, so a single elected lane issues a single UBLKCP.
+  constexpr uint32_t kStageBytes = (uint32_t)(SM::ROWS * kStageFrames * sizeof(CT));
+  auto issue_chunk = [&](int bin, int c, unsigned n) {  // warp 0
+    if (lane == 0) {
+      const int st = n & 1u;
+      mbar_expect_tx(&sm.full[st], kStageBytes);
+      bulk_g2s(&sm.zbuf[st][0][0], zbase + ((size_t)bin * nchunks + c) * (SM::ROWS * kStageFrames), kStageBytes,
                &sm.full[st]);
+    }
   };
   if (g == 0 && cur < total) issue_chunk(cur % F, 0, 0);
 
 #ifdef PBB_PHASE_TIMING
   long long _tp = clock64();
 #endif
+  // lean variant: the model of a task can be prefetched (cp.async, L2 -> smem) during the previous
+  // task's last chunk; cb = buffer holding the current task's model, pf = it is already there
+  int cb = 0;
+  bool pf = false;
   while (cur < total) {
     const int it = cur / F, bin = cur - it * F;
     const bool mstep_only = a.first_is_m && it == 0;
     const bool last_it = it == a.iterations - 1;
-    if (tid == 0) {
-      sm.tick[1] = atomicAdd(a.ticket, 1);  // the task after this one (prefetch target)
-      if (!mstep_only) {
+    int tnext = 0;
+    if (tid == 0) tnext = atomicAdd(a.ticket, 1);  // the task after this one; consumed a chunk later
+    if (!mstep_only && !pf) {
+      if (tid == 0) {
         while (ld_acquire_gpu(a.flags + bin) < it) __nanosleep(40);
       }
-    }
-    __syncthreads();
-    PBB_PH(0);  // ticket + flag wait
-    const int nxt = sm.tick[1];  // read before any later barrier; rewritten only after them
-    if (!mstep_only) {
+      __syncthreads();
+      PBB_PH(0);  // flag wait
       const double* __restrict__ cf = a.coef + (size_t)bin * K * NS;
-      for (int i = tid; i < K * NS; i += blockDim.x) (&sm.coef[0][0])[i] = __ldcg(cf + i);
+      for (int i = tid; i < K * NS; i += blockDim.x) (&sm.coef[cb][0][0])[i] = __ldcg(cf + i);
+      if (FULL) {
+        if (tid < K) {
+          sm.ew[cb][tid] = __ldcg(a.ew + (size_t)bin * K + tid);
+          sm.ld[tid] = __ldcg(a.ld + (size_t)bin * K + tid);
+          sm.w[tid] = __ldcg(a.w + (size_t)bin * K + tid);
+        }
+      } else if (tid < 8) {
+        sm.raw[cb][tid] = __ldcg((tid < 4 ? a.ew : a.ld) + (size_t)bin * 4 + (tid & 3));
+      }
+    } else if (pf) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    if (!FULL && !mstep_only && tid < 32) {
+      // weights and ew from the published raw scalars (sum of gamma, log det): all of it lives in warp 0
+      __syncwarp();
       if (tid < K) {
-        sm.ew[tid] = __ldcg(a.ew + (size_t)bin * K + tid);
-        sm.ld[tid] = __ldcg(a.ld + (size_t)bin * K + tid);
-        sm.w[tid] = __ldcg(a.w + (size_t)bin * K + tid);
+        double ldmin = sm.raw[cb][4];
+#pragma unroll
+        for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, sm.raw[cb][4 + j]);
+        const double wk = a.weight_mode == PBB_WEIGHT_CONST ? 1.0 / K : sm.raw[cb][tid] / (double)T;
+        sm.ew[cb][tid] = wk * exp(ldmin - sm.raw[cb][4 + tid]);
       }
     }
     const bool fast = FULL ? (a.softmax_fast && !(a.user_model && it == 0)) : true;
@@ -599,20 +623,58 @@ em_persistent_kernel(const PersistArgs a) {
 #pragma unroll
     for (int k = 0; k < K; ++k) sg[k] = 0.0;
     int buf = 0;
+    bool pf_next = false;
+    int probe = -1;
 
     __syncthreads();  // model staged
+    PBB_PH(7);  // task start -> model staged
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
       // The stage refilled below was last read in the previous chunk.  In the E+M loops every
       // observation load of a step precedes that step's exchange barrier, so once warp 0 is
       // here all warps are done with it; only the M-step-only loop (no exchange) needs a barrier.
       if (!lean) __syncthreads();
+      const bool last_chunk = c + 1 == nchunks;
+      // Thread 0 walks the next ticket through three chunk tops so that neither the ticket atomic
+      // nor the flag probe (L2 round trips) is waited for: consume the ticket and issue the probe at
+      // chunk n-3, publish both to shared memory at chunk n-2, everybody reads them at chunk n-1.
+      if (tid == 0) {
+        const int c_probe = nchunks >= 3 ? nchunks - 3 : -1;
+        const int c_pub = nchunks >= 2 ? nchunks - 2 : 0;
+        if (c == c_probe && !FULL && tnext < total) {
+          const int ni = tnext / F, nb = tnext - ni * F;
+          probe = (a.first_is_m && ni == 0) ? -1 : ld_acquire_gpu(a.flags + nb) - ni;  // >= 0: published
+        }
+        if (c == c_pub) {
+          sm.tick[1] = tnext;
+          sm.ready = (!FULL && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
+        }
+      }
       if (g == 0) {
-        if (c + 1 < nchunks) issue_chunk(bin, c + 1, chunk_cnt + 1);
-        else if (nxt < total) issue_chunk(nxt % F, 0, chunk_cnt + 1);
+        if (!last_chunk) {
+          issue_chunk(bin, c + 1, chunk_cnt + 1);
+        } else {
+          const int nx = __shfl_sync(0xffffffffu, tnext, 0);
+          if (nx < total) issue_chunk(nx % F, 0, chunk_cnt + 1);
+        }
+      }
+      if (!FULL && lean && last_chunk && nchunks >= 3 && sm.ready) {
+        // prefetch the next task's model into the other buffer (16-byte L2 -> smem copies)
+        pf_next = true;
+        const int nb = sm.tick[1] % F;
+        const char* __restrict__ src = reinterpret_cast<const char*>(a.coef + (size_t)nb * K * NS);
+        char* dst = reinterpret_cast<char*>(&sm.coef[cb ^ 1][0][0]);
+        for (int i = tid; i < K * NS / 2; i += blockDim.x)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 16 * i)), "l"(src + 16 * i)
+                       : "memory");
+        if (tid < 4)  // (sum gamma)[4] from a.ew, (ld)[4] from a.ld, two 16-byte pieces each
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(
+                           reinterpret_cast<char*>(&sm.raw[cb ^ 1][0]) + 16 * tid)),
+                       "l"(reinterpret_cast<const char*>((tid < 2 ? a.ew : a.ld) + (size_t)nb * 4) + 16 * (tid & 1))
+                       : "memory");
       }
       const int st = chunk_cnt & 1u;
-      PBB_PH(1);  // staging / chunk barrier
+      PBB_PH(1);  // staging / chunk top
       mbar_wait(&sm.full[st], (chunk_cnt >> 1) & 1u);
       PBB_PH(2);  // TMA wait
       ++chunk_cnt;
@@ -620,12 +682,12 @@ em_persistent_kernel(const PersistArgs a) {
       const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
       if (lean) {
         if constexpr (FPL == 2) {
-          lean_chunk2<D, K, CT>(sm, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk2<D, K, CT>(sm, cb, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
           if (nsteps & 1) {  // odd tail step of a short last chunk
-            lean_chunk<D, K, CT>(sm, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
+            lean_chunk<D, K, CT>(sm, cb, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
           }
         } else {
-          lean_chunk<D, K, CT>(sm, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk<D, K, CT>(sm, cb, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
         }
       }
       else general_chunk<D, K, CT, FULL>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
@@ -636,7 +698,7 @@ em_persistent_kernel(const PersistArgs a) {
       double q1[K], gp[K], cp[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) q1[k] = 0.0;
-      softmax_product<D, K>(q1, sm.ew, a.aff_eps, gp, cp);
+      softmax_product<D, K>(q1, sm.ew[cb], a.aff_eps, gp, cp);
       const int npad_lane = (lane >= 32 - (zs - T)) ? 1 : 0;  // zs - T < 32: last step's tail lanes
 #pragma unroll
       for (int k = 0; k < K; ++k) sg[k] -= npad_lane ? gp[k] : 0.0;
@@ -736,34 +798,46 @@ em_persistent_kernel(const PersistArgs a) {
           __syncwarp();
           ldk = model_from_eig_warp(sm.V[k], sm.lam[k], sm.tab, D, lane, co);
         }
-        if (lane == 0) sm.ld[k] = ldk;
+        if (lane == 0) {
+          sm.ld[k] = ldk;
+          if (!FULL) {
+            a.ld[(size_t)bin * 4 + k] = ldk;
+            a.ew[(size_t)bin * 4 + k] = sm.S[k][NS];
+          }
+        }
       }
       __syncthreads();
       PBB_PH(5);  // update (Gauss-Jordan)
-      if (tid < K) {
-        const int k = tid;
-        double wk;
-        if (a.weight_mode == PBB_WEIGHT_CONST) wk = 1.0 / K;
-        else if (!(FULL && a.saliency != nullptr)) wk = sm.S[k][NS] / (double)T;
-        else {
+      // publish with a single cumulative gpu-scope release; the CTA barrier above ordered every
+      // warp's model stores before it.  Lean variant: the class warps already stored the raw
+      // scalars (sum of gamma, log det) and the consumer derives weights / ew itself.
+      if (tid == 0) {
+        if (FULL) {
+          double ldmin = sm.ld[0];
+          for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, sm.ld[j]);
           double n1 = 0.0;
           for (int j = 0; j < K; ++j) n1 += fabs(sm.S[j][NS]);
-          wk = sm.S[k][NS] / (n1 == 0.0 ? 1e-10 : n1);
+          for (int k = 0; k < K; ++k) {
+            double wk;
+            if (a.weight_mode == PBB_WEIGHT_CONST) wk = 1.0 / K;
+            else if (a.saliency == nullptr) wk = sm.S[k][NS] / (double)T;
+            else wk = sm.S[k][NS] / (n1 == 0.0 ? 1e-10 : n1);
+            a.w[(size_t)bin * K + k] = wk;
+            a.ld[(size_t)bin * K + k] = sm.ld[k];
+            a.ew[(size_t)bin * K + k] = wk * exp(ldmin - sm.ld[k]);
+          }
         }
-        double ldmin = sm.ld[0];
-        for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, sm.ld[j]);
-        a.w[(size_t)bin * K + k] = wk;
-        a.ld[(size_t)bin * K + k] = sm.ld[k];
-        a.ew[(size_t)bin * K + k] = wk * exp(ldmin - sm.ld[k]);
+        st_release_gpu(a.flags + bin, it + 1);
       }
-      // CTA barrier, then ONE gpu-scope release by thread 0 (the cooperative-groups grid-sync
-      // pattern): the barrier orders every thread's model stores before the cumulative release.
-      __syncthreads();
-      if (tid == 0) st_release_gpu(a.flags + bin, it + 1);
       PBB_PH(6);  // weights + publish
     }
-    cur = nxt;
+    // all threads read the next ticket (published one chunk before the end of the pass)
+    cur = sm.tick[1];
+    pf = pf_next;
+    if (pf_next) cb ^= 1;
+    // no barrier needed here: tick / ld / S are next written behind later barriers of the next task
   }
 }
+
 
 }  // namespace pbb
