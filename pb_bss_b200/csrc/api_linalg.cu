@@ -31,7 +31,7 @@ __global__ void heig_batched_kernel(const double2* __restrict__ a, int n, int D,
     A[i] = h;
   }
   __syncwarp();
-  const int sweeps = warp_jacobi(A, V, rot, D, lane);
+  const int sweeps = warp_jacobi_any(A, V, rot, D, lane);
   if ((__any_sync(0xffffffffu, bad) || sweeps > kJacobiMaxSweeps) && lane == 0 && status) atomicMax(status, m + 1);
   for (int x = lane; x < D; x += 32) {
     const int r = eig_rank(A, D, x);

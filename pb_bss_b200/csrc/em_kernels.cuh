@@ -538,7 +538,7 @@ __global__ void cacg_update_kernel(const UpdArgs u) {
       __syncwarp();
     }
     // 3. eigendecomposition                                (cacg.py:95)
-    warp_jacobi(A, V, rot, D, lane);
+    warp_jacobi_any(A, V, rot, D, lane);
     // 4. normalise + floor                                 (cacg.py:111-126)
     double lmax = -INFINITY;
     for (int d = lane; d < D; d += 32) lmax = fmax(lmax, A[d * D + d].x);
@@ -756,7 +756,7 @@ __global__ void cw_update_kernel(const CwUpdArgs u) {
     }
     __syncwarp();
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(u.status, f + 1);
-    warp_jacobi(A, V, rot, D, lane);
+    warp_jacobi_any(A, V, rot, D, lane);
     // largest eigenvalue; ties resolved like "last of the ascending order"
     int best = 0;
     double lmax = A[0].x;

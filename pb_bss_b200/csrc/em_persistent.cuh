@@ -783,7 +783,7 @@ em_persistent_kernel(const PersistArgs a) {
             for (int i = lane; i < NS; i += 32) { A[i].x *= tn / D; A[i].y *= tn / D; }
             __syncwarp();
           }
-          warp_jacobi(A, sm.V[k], sm.rot[k], D, lane);
+          warp_jacobi_small<D>(A, sm.V[k], lane);
           double lmax = -INFINITY;
           for (int d = lane; d < D; d += 32) lmax = fmax(lmax, A[d * D + d].x);
 #pragma unroll

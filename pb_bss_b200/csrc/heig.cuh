@@ -126,6 +126,98 @@ __device__ inline int warp_jacobi(double2* __restrict__ A, double2* __restrict__
   return sweep + 1;
 }
 
+// Same algorithm for compile-time D <= 8: one lane per (pair, row/column) task -- D/2 pairs x D
+// entries fit one warp -- every lane derives its pair's rotation itself (no staging through
+// shared memory, no integer division, no task loops): 3 warp syncs per round.
+template <int D>
+__device__ __forceinline__ int warp_jacobi_small(double2* __restrict__ A, double2* __restrict__ V, int lane) {
+  static_assert(D >= 2 && D <= 8, "small-D Jacobi");
+  constexpr int n = D + (D & 1), npair = n / 2, m = n - 1;
+  const double eps2 = DBL_EPSILON * DBL_EPSILON;
+  for (int i = lane; i < D * D; i += 32) V[i] = make_double2((i / D == i % D) ? 1.0 : 0.0, 0.0);
+  __syncwarp();
+  const int pi = lane / D, idx = lane - pi * D;  // pair index within the round, row / column index
+  const bool lane_on = pi < npair;
+  int sweep = 0;
+  for (; sweep < kJacobiMaxSweeps; ++sweep) {
+    unsigned rotated = 0;
+#pragma unroll 1
+    for (int r = 0; r < m; ++r) {
+      int p = 0, q = 0;
+      bool act = false;
+      double c = 1.0, sr = 0.0, si = 0.0, an = 0.0, dn = 0.0;
+      if (lane_on) {
+        if (pi == 0) { p = r % m; q = n - 1; }
+        else { p = (r + pi) % m; q = (r - pi + m) % m; }
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q < D) {
+          const double a = A[p * D + p].x, d = A[q * D + q].x;
+          const double2 b = A[p * D + q];
+          const double m2 = b.x * b.x + b.y * b.y;
+          if (m2 > eps2 * fabs(a * d) && m2 > 1e-300) {
+            act = true;
+            const double dl = 0.5 * (d - a);
+            const double sg = dl >= 0.0 ? 1.0 : -1.0;
+            const double h = fabs(dl) + sqrt(dl * dl + m2);
+            const double w = rsqrt(h * h + m2);
+            c = h * w;
+            sr = sg * b.x * w;
+            si = sg * b.y * w;
+            const double tb = sg * m2 / h;
+            an = a - tb;
+            dn = d + tb;
+          }
+        }
+      }
+      const unsigned any = __ballot_sync(0xffffffffu, act);
+      rotated |= any;
+      if (any == 0) continue;
+      __syncwarp();  // everyone has read the pivots
+      // column update X <- X J for row idx of A and of V
+      if (act) {
+        const double2 xp = A[idx * D + p], xq = A[idx * D + q];
+        A[idx * D + p] = make_double2(c * xp.x - (sr * xq.x + si * xq.y), c * xp.y - (sr * xq.y - si * xq.x));
+        A[idx * D + q] = make_double2(c * xq.x + (sr * xp.x - si * xp.y), c * xq.y + (sr * xp.y + si * xp.x));
+        const double2 vp = V[idx * D + p], vq = V[idx * D + q];
+        V[idx * D + p] = make_double2(c * vp.x - (sr * vq.x + si * vq.y), c * vp.y - (sr * vq.y - si * vq.x));
+        V[idx * D + q] = make_double2(c * vq.x + (sr * vp.x - si * vp.y), c * vq.y + (sr * vp.y + si * vp.x));
+      }
+      __syncwarp();
+      // row update A <- J^H A for column idx
+      if (act) {
+        const double2 ap = A[p * D + idx], aq = A[q * D + idx];
+        A[p * D + idx] = make_double2(c * ap.x - (sr * aq.x - si * aq.y), c * ap.y - (sr * aq.y + si * aq.x));
+        A[q * D + idx] = make_double2(c * aq.x + (sr * ap.x + si * ap.y), c * aq.y + (sr * ap.y - si * ap.x));
+      }
+      __syncwarp();
+      if (act && idx == 0) {  // exact values for the rotated 2x2 block
+        A[p * D + q] = make_double2(0.0, 0.0);
+        A[q * D + p] = make_double2(0.0, 0.0);
+        A[p * D + p] = make_double2(an, 0.0);
+        A[q * D + q] = make_double2(dn, 0.0);
+      }
+      __syncwarp();
+    }
+    if (rotated == 0) break;
+  }
+  return sweep + 1;
+}
+
+// dispatch on the runtime dimension: templated path for D <= 8, generic otherwise
+__device__ inline int warp_jacobi_any(double2* __restrict__ A, double2* __restrict__ V, double* __restrict__ rot,
+                                      int D, int lane) {
+  switch (D) {
+    case 2: return warp_jacobi_small<2>(A, V, lane);
+    case 3: return warp_jacobi_small<3>(A, V, lane);
+    case 4: return warp_jacobi_small<4>(A, V, lane);
+    case 5: return warp_jacobi_small<5>(A, V, lane);
+    case 6: return warp_jacobi_small<6>(A, V, lane);
+    case 7: return warp_jacobi_small<7>(A, V, lane);
+    case 8: return warp_jacobi_small<8>(A, V, lane);
+    default: return warp_jacobi(A, V, rot, D, lane);
+  }
+}
+
 // rank of eigenvalue i in ascending order (stable), for i < D; lanes >= D get -1.
 // For D > 32 callers loop (i = lane, lane + 32, ...).
 __device__ inline int eig_rank(const double2* A, int D, int i) {

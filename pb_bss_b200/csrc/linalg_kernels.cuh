@@ -129,7 +129,7 @@ __global__ void gev_kernel(const double2* __restrict__ a, const double2* __restr
     C[i] = make_double2(0.5 * (u.x + v.x), r == c ? 0.0 : 0.5 * (-u.y + v.y));
   }
   __syncwarp();
-  const int sweeps = warp_jacobi(C, V, rot, D, lane);
+  const int sweeps = warp_jacobi_any(C, V, rot, D, lane);
   int best = 0;
   double lmax = C[0].x;
   for (int d = 1; d < D; ++d) {

@@ -1,0 +1,45 @@
+"""Device-resident timings of the BASELINE.json configs other than C2 (C1, C4, C5-like per-utterance pipeline)."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, '.')
+from oracle import synth
+from pb_bss_b200.distribution import CACGMMTrainer, CWMMTrainer
+from pb_bss_b200 import extraction as E
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+# C1
+F, T, D, K, I = 129, 200, 4, 2, 20
+y = torch.from_numpy(synth.noise_stft(F, T, D)).cuda(); init = torch.from_numpy(synth.init_affiliation(F, K, T)).cuda()
+ms, _ = timed(lambda: CACGMMTrainer().fit(y, initialization=init, iterations=I))
+print(f'C1 cACGMM F=129 T=200 D=4 K=2 I=20: {ms:.3f} ms -> {I/ms*1e3:.0f} it/s')
+# C4
+F, T, D, K, I = 257, 1000, 6, 4, 50
+y = torch.from_numpy(synth.noise_stft(F, T, D, seed=4)).cuda(); init = torch.from_numpy(synth.init_affiliation(F, K, T)).cuda()
+tr = CWMMTrainer()
+ms, m = timed(lambda: tr.fit(y, initialization=init, iterations=I))
+print(f'C4 CWMM  F=257 T=1000 D=6 K=4 I=50: {ms:.3f} ms -> {I/ms*1e3:.0f} it/s, {I*F*T/ms*1e3:.3e} frames*bins/s')
+# C5-like: one utterance K=2 cACGMM + PSD + Souden-MVDR / PCA-MVDR
+F, T, D, K, I = 513, 500, 8, 2, 100
+y = torch.from_numpy(synth.noise_stft(F, T, D, seed=5)).cuda(); init = torch.from_numpy(synth.init_affiliation(F, K, T)).cuda()
+def c5():
+    model = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+    aff = model.predict(y)
+    Y = y.transpose(-1, -2).contiguous()
+    psd = E.get_power_spectral_density_matrix(Y, aff)
+    w = E.get_mvdr_vector(E.get_pca_vector(psd[:, 0]), psd[:, 1].contiguous())
+    return E.apply_beamforming_vector(w, Y)
+ms, _ = timed(c5)
+print(f'C5 per utterance (K=2 fit 100 it + predict + PSD + PCA + MVDR + apply): {ms:.3f} ms')
+ms, _ = timed(lambda: CACGMMTrainer().fit(y, initialization=init, iterations=I))
+print(f'   of which fit: {ms:.3f} ms -> {I/ms*1e3:.0f} it/s')
+a = torch.from_numpy(synth.pos_def_hermitian(1539, 8, 8)).cuda(); b = torch.from_numpy(synth.pos_def_hermitian(1539, 8, 8, seed=2)).cuda()
+from pb_bss_b200.extraction.linalg import eigh
+ms, _ = timed(lambda: eigh(a)); print(f'eigh 1539 x 8x8: {ms*1e3:.1f} us')
+ms, _ = timed(lambda: E.get_gev_vector(a, b)); print(f'gev  1539 x 8x8: {ms*1e3:.1f} us')
