@@ -238,6 +238,30 @@ static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
                                    sizeof(PersistSmem<D, K, CT>), &cache_lean, a, "em_persistent_kernel", st);
 }
 
+// complex Watson EM on the persistent kernel (lean structure, MODEL = 1)
+template <int D, int K, typename CT>
+static int launch_persist_cw_t(const PersistArgs& a, cudaStream_t st) {
+  static int cache = 0;
+  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL, 1>, 32 * (D / 2),
+                                   sizeof(PersistSmem<D, K, CT>), &cache, a, "em_persistent_kernel_cw", st);
+}
+template <int D>
+static int launch_persist_cw_d(const PersistArgs& a, int K, int dtype, cudaStream_t st) {
+  const bool c128 = dtype == PBB_C128;
+  switch (K) {
+    case 2: return c128 ? launch_persist_cw_t<D, 2, double2>(a, st) : launch_persist_cw_t<D, 2, float2>(a, st);
+    case 3: return c128 ? launch_persist_cw_t<D, 3, double2>(a, st) : launch_persist_cw_t<D, 3, float2>(a, st);
+    default: return c128 ? launch_persist_cw_t<D, 4, double2>(a, st) : launch_persist_cw_t<D, 4, float2>(a, st);
+  }
+}
+static int launch_persist_cw(const PersistArgs& a, int D, int K, int dtype, cudaStream_t st) {
+  switch (D) {
+    case 4: return launch_persist_cw_d<4>(a, K, dtype, st);
+    case 6: return launch_persist_cw_d<6>(a, K, dtype, st);
+    default: return launch_persist_cw_d<8>(a, K, dtype, st);
+  }
+}
+
 template <int D, int K>
 static int launch_persist_dk(const PersistArgs& a, int dtype, bool full, cudaStream_t st) {
   if (dtype == PBB_C128) return launch_persist_t<D, K, double2>(a, full, st);
@@ -539,8 +563,14 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
-  int r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
-                            : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
+  const bool persistent = fast_shape(D, K) && saliency == nullptr;
+  int r;
+  if (persistent)
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, st);
+  else
+    r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
+                          : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
   if (r) return r;
   EmArgs a;
   memset(&a, 0, sizeof(a));
@@ -564,6 +594,22 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
     PBB_CUDA(cudaMemcpyAsync(&ends[1], spline_t + spline_n + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
     PBB_CUDA(cudaStreamSynchronize(st));
     u.spline.x_lo = ends[0]; u.spline.x_hi = ends[1];
+  }
+  if (persistent) {
+    // every EM iteration in one launch (em_persistent.cuh, MODEL = 1); the last iteration's raw
+    // scatter sums go through cw_update_kernel for the reference-exact mode / concentration / weight
+    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
+    PersistArgs p;
+    memset(&p, 0, sizeof(p));
+    p.z = ws.z; p.zs = ws.zs; p.F = F; p.T = T;
+    p.iterations = iterations; p.first_is_m = 1; p.user_model = 0; p.softmax_fast = 0;
+    p.aff_in = init_aff; p.aff_eps = 0.0; p.weight_mode = weight_mode;
+    p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
+    p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status; p.phase = ws.phase;
+    p.spline = u.spline;
+    if ((r = launch_persist_cw(p, D, K, dtype, st))) return r;
+    u.nch = 1;
+    return launch_cw_update(u, st);
   }
   for (int it = 0; it < iterations; ++it) {
     if (it == 0) { a.mode = kModeM; a.aff_in = init_aff; a.q_in = nullptr; }

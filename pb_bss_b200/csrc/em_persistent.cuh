@@ -65,6 +65,7 @@ struct PersistArgs {
   int* flags;    // (F) number of model updates published for the bin
   int* ticket;   // (1)
   int* status;
+  CwSpline spline;  // complex Watson only: inverse hypergeometric ratio (model_kind 1)
   unsigned long long* phase;  // debug: per-phase cycle sums (PBB_PHASE_TIMING builds)
 };
 
@@ -139,7 +140,7 @@ struct PersistSmem {
   double coef[2][K][NS];  // E-step form of the bin's model (double buffered: next task's model is prefetched)
   double xq[2][M][2 * K][32];  // partial quadratic forms, up to 2 frames per lane
   double S[K][NS + 1];  // scatter sums + sum of gamma
-  double rot[K][((D + 1) / 2) * 6];
+  alignas(16) double rot[K][((D + 1) / 2) * 6];
   double lam[K][D];
   double ld[K], w[K];
   alignas(16) double ew[2][4];  // w_k exp(ld_min - ld_k) of the current / prefetched model
@@ -230,13 +231,41 @@ __device__ __forceinline__ void softmax_product(double (&q)[K], const double* __
   }
 }
 
+// Complex Watson posterior (complex_watson.py:73-87 + mixture_model_utils.py:7-55, eps = 0):
+// log_pdf_k = kappa_k |m_k^H z|^2 - log c(kappa_k); q_k arrives as the slot form of m m^H.
+// The M-step weight is gamma itself (complex_watson.py:307-312 has no 1/q).
+template <int K>
+__device__ __forceinline__ void softmax_watson(const double (&q)[K], const double* __restrict__ kappa,
+                                               const double* __restrict__ lognorm, const double* __restrict__ w,
+                                               double (&gam)[K], double (&cw)[K]) {
+  double lp[K];
+  double m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    lp[k] = fma(kappa[k], q[k], -lognorm[k]);
+    m = lp[k] > m ? lp[k] : m;
+  }
+  double den = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    gam[k] = exp(lp[k] - m) * w[k];
+    den += gam[k];
+  }
+  const double inv = 1.0 / fmax(den, kTiny);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    gam[k] *= inv;
+    cw[k] = gam[k];
+  }
+}
+
 // Hot loop of the lean variant: E-step + M-step of one ring stage for slot
 // group g.  All warps run the same instructions (one loop body in the L0
 // instruction cache); the staged rows are laid out so that the group's local
 // channels are rows 2g .. 2g+NLOC-1, i.e. one base register plus immediates.
 // No per-frame masking: padded frames have z = 0, add nothing to the scatter
 // sums, and their gamma is subtracted analytically by the caller.
-template <int D, int K, typename CT>
+template <int D, int K, typename CT, int MODEL>
 __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps, int lane,
                                            int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
                                            double (&sg)[K], int j0 = 0) {
@@ -279,7 +308,8 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, in
     }
     buf ^= 1;
     double gam[K], cw[K];
-    softmax_product<D, K>(q, sm.ew[cb], eps, gam, cw);
+    if constexpr (MODEL == 1) softmax_watson<K>(q, sm.ew[cb], sm.ld, sm.w, gam, cw);
+    else softmax_product<D, K>(q, sm.ew[cb], eps, gam, cw);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       sg[k] += gam[k];
@@ -293,7 +323,7 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, in
 // the coefficient loads, the barrier and the loop overhead are shared by the two
 // frames, and their E-step / softmax dependency chains interleave, which is what
 // keeps the fp64 pipe busy with only two warps per scheduler.
-template <int D, int K, typename CT>
+template <int D, int K, typename CT, int MODEL>
 __device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps2, int lane,
                                             int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
                                             double (&sg)[K]) {
@@ -349,8 +379,13 @@ __device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int cb, i
     }
     buf ^= 1;
     double gA[K], cA[K], gB[K], cB[K];
-    softmax_product<D, K>(qA, sm.ew[cb], eps, gA, cA);
-    softmax_product<D, K>(qB, sm.ew[cb], eps, gB, cB);
+    if constexpr (MODEL == 1) {
+      softmax_watson<K>(qA, sm.ew[cb], sm.ld, sm.w, gA, cA);
+      softmax_watson<K>(qB, sm.ew[cb], sm.ld, sm.w, gB, cB);
+    } else {
+      softmax_product<D, K>(qA, sm.ew[cb], eps, gA, cA);
+      softmax_product<D, K>(qB, sm.ew[cb], eps, gB, cB);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       sg[k] += gA[k] + gB[k];
@@ -532,7 +567,7 @@ __device__ __forceinline__ double warp_hpd_inverse(double2* __restrict__ A, int 
   return det;
 }
 
-template <int D, int K, typename CT, bool FULL, int FPL>
+template <int D, int K, typename CT, bool FULL, int FPL, int MODEL = 0>
 __global__ void __launch_bounds__(32 * (D / 2), (FPL == 2 ? (D == 8 ? 2 : (D == 6 ? 2 : 4)) : (D == 8 ? 3 : (D == 6 ? 4 : 6))))
 em_persistent_kernel(const PersistArgs a) {
   using SM = PersistSmem<D, K, CT>;
@@ -596,13 +631,19 @@ em_persistent_kernel(const PersistArgs a) {
           sm.ld[tid] = __ldcg(a.ld + (size_t)bin * K + tid);
           sm.w[tid] = __ldcg(a.w + (size_t)bin * K + tid);
         }
+      } else if (MODEL == 1) {
+        if (tid < K) {
+          sm.ew[cb][tid] = __ldcg(a.ew + (size_t)bin * 4 + tid);  // kappa
+          sm.ld[tid] = __ldcg(a.ld + (size_t)bin * 4 + tid);      // log norm
+          sm.w[tid] = __ldcg(a.w + (size_t)bin * K + tid);
+        }
       } else if (tid < 8) {
         sm.raw[cb][tid] = __ldcg((tid < 4 ? a.ew : a.ld) + (size_t)bin * 4 + (tid & 3));
       }
     } else if (pf) {
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
-    if (!FULL && !mstep_only && tid < 32) {
+    if (!FULL && MODEL == 0 && !mstep_only && tid < 32) {
       // weights and ew from the published raw scalars (sum of gamma, log det): all of it lives in warp 0
       __syncwarp();
       if (tid < K) {
@@ -647,7 +688,7 @@ em_persistent_kernel(const PersistArgs a) {
         }
         if (c == c_pub) {
           sm.tick[1] = tnext;
-          sm.ready = (!FULL && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
+          sm.ready = (!FULL && MODEL == 0 && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
         }
       }
       if (g == 0) {
@@ -682,24 +723,33 @@ em_persistent_kernel(const PersistArgs a) {
       const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
       if (lean) {
         if constexpr (FPL == 2) {
-          lean_chunk2<D, K, CT>(sm, cb, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk2<D, K, CT, MODEL>(sm, cb, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
           if (nsteps & 1) {  // odd tail step of a short last chunk
-            lean_chunk<D, K, CT>(sm, cb, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
+            lean_chunk<D, K, CT, MODEL>(sm, cb, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
           }
         } else {
-          lean_chunk<D, K, CT>(sm, cb, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk<D, K, CT, MODEL>(sm, cb, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
         }
       }
       else general_chunk<D, K, CT, FULL>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
       PBB_PH(3);  // EM steps
     }
-    if (lean && zs > T) {
+    if (lean && MODEL == 0 && zs > T) {
       // the zs - T padded frames of every row behaved like zero observations
       double q1[K], gp[K], cp[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) q1[k] = 0.0;
       softmax_product<D, K>(q1, sm.ew[cb], a.aff_eps, gp, cp);
       const int npad_lane = (lane >= 32 - (zs - T)) ? 1 : 0;  // zs - T < 32: last step's tail lanes
+#pragma unroll
+      for (int k = 0; k < K; ++k) sg[k] -= npad_lane ? gp[k] : 0.0;
+    }
+    if (lean && MODEL == 1 && zs > T) {
+      double q1[K], gp[K], cp[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) q1[k] = 0.0;
+      softmax_watson<K>(q1, sm.ew[cb], sm.ld, sm.w, gp, cp);
+      const int npad_lane = (lane >= 32 - (zs - T)) ? 1 : 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) sg[k] -= npad_lane ? gp[k] : 0.0;
     }
@@ -735,6 +785,42 @@ em_persistent_kernel(const PersistArgs a) {
       for (int k = g; k < K; k += M) {
         double2* A = sm.A[k];
         double* Ad = reinterpret_cast<double*>(A);
+        if constexpr (MODEL == 1) {
+          // complex Watson: covariance = S / sum(gamma) (complex_watson.py:307-312), mode = eigenvector of
+          // the largest eigenvalue (pb_bss/utils.py:154-163), concentration from the spline (:314)
+          const double wscale = 1.0 / sm.S[k][NS];
+          bool wbad = false;
+          for (int s = lane; s < NS; s += 32) {
+            const int pk = sm.tab[s];
+            const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
+            const double v = sm.S[k][s] * wscale;
+            wbad |= !isfinite(v);
+            if (kind == 0) { Ad[2 * (d * D + d)] = v; Ad[2 * (d * D + d) + 1] = 0.0; }
+            else if (kind == 1) { Ad[2 * (d * D + e)] = v; Ad[2 * (e * D + d)] = v; }
+            else { Ad[2 * (d * D + e) + 1] = -v; Ad[2 * (e * D + d) + 1] = v; }
+          }
+          __syncwarp();
+          if (__any_sync(0xffffffffu, wbad) && lane == 0) atomicMax(a.status, bin + 1);
+          warp_jacobi_small<D>(A, sm.V[k], lane);
+          int best = 0;
+          double lmax = A[0].x;
+#pragma unroll
+          for (int d = 1; d < D; ++d) {
+            const double l = A[d * D + d].x;
+            if (l >= lmax) { lmax = l; best = d; }
+          }
+          double2* mloc = reinterpret_cast<double2*>(sm.rot[k]);  // ((D+1)/2)*6 doubles >= 2*D, 16-byte aligned
+          __syncwarp();
+          for (int d = lane; d < D; d += 32) mloc[d] = sm.V[k][d * D + best];
+          __syncwarp();
+          cw_coef_from_mode(mloc, sm.tab, D, lane, a.coef + ((size_t)bin * K + k) * NS);
+          if (lane == 0) {
+            const double kappa = cw_spline_eval(a.spline, lmax);
+            a.ew[(size_t)bin * 4 + k] = kappa;
+            a.ld[(size_t)bin * 4 + k] = cw_log_norm(kappa, D);
+          }
+          continue;
+        }
         const double scale = (double)D / fmax(sm.S[k][NS], kTiny);
         bool bad = false;
         auto build = [&]() {
@@ -812,7 +898,13 @@ em_persistent_kernel(const PersistArgs a) {
       // warp's model stores before it.  Lean variant: the class warps already stored the raw
       // scalars (sum of gamma, log det) and the consumer derives weights / ew itself.
       if (tid == 0) {
-        if (FULL) {
+        if (MODEL == 1) {
+          double n1 = 0.0;
+          for (int j = 0; j < K; ++j) n1 += fabs(sm.S[j][NS]);
+          for (int k = 0; k < K; ++k)
+            a.w[(size_t)bin * K + k] =
+                a.weight_mode == PBB_WEIGHT_CONST ? 1.0 / K : sm.S[k][NS] / (n1 == 0.0 ? 1e-10 : n1);
+        } else if (FULL) {
           double ldmin = sm.ld[0];
           for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, sm.ld[j]);
           double n1 = 0.0;
