@@ -44,6 +44,7 @@ struct CacgmmWorkspace {
   int* flags;   // (F) per-bin model version, persistent kernel
   int* ticket;  // (1)
   unsigned long long* phase;  // (16) debug phase counters
+  int* dead;    // (F) bins with an all-zero observation frame
   double* part;
   double* coef;
   double* ld;
@@ -66,6 +67,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t z_staged = (size_t)F * nchunks * stage_rows(D % 2 == 0 ? D : D + 1) * kStageFrames * sizeof(double2);
   const size_t o_z = take(z_plain > z_staged ? z_plain : z_staged);
   const size_t o_flags = take((size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8);
+  const size_t o_dead = take((size_t)F * sizeof(int));
   const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
   const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
   const size_t o_ld = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
@@ -77,6 +79,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   ws.zs = zs;
   ws.flags = reinterpret_cast<int*>(b + o_flags);
   ws.ticket = ws.flags + F;
+  ws.dead = reinterpret_cast<int*>(b + o_dead);
   ws.phase = reinterpret_cast<unsigned long long*>(b + o_flags + (((size_t)(F + 1) * sizeof(int) + 7) / 8) * 8);
   ws.part = reinterpret_cast<double*>(b + o_part);
   ws.coef = reinterpret_cast<double*>(b + o_coef);
@@ -102,14 +105,15 @@ static int launch_normalize(const void* y, void* z, int F, int T, int D, int swa
 }
 
 template <typename CT>
-static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, cudaStream_t st) {
+static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, int* dead, cudaStream_t st) {
+  if (dead != nullptr) PBB_CUDA(cudaMemsetAsync(dead, 0, (size_t)F * sizeof(int), st));
   const int block = 64;  // divides kStageFrames
   const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
   dim3 grid(nchunks * (kStageFrames / block), F);
   const size_t smem = (size_t)block * (D + 1) * sizeof(double2);
   LaunchScope ls("normalize_staged_kernel", st);
   normalize_staged_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T, D,
-                                                          stage_rows(D), kStageFrames, nchunks);
+                                                          stage_rows(D), kStageFrames, nchunks, dead);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -357,8 +361,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   const bool persistent = fast_shape(D, K) && !(opt->reserved & 1);
   int r;
   if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
-    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, st)
-                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, st);
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, st);
   else
     r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
                           : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
@@ -408,7 +412,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     p.covariance_norm = opt->covariance_norm; p.weight_mode = opt->weight_mode;
     p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
-    p.phase = ws.phase;
+    p.phase = ws.phase; p.dead = ws.dead;
     // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
     const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
     const bool full = saliency != nullptr || activity != nullptr || !lean_ok || p.user_model;
@@ -566,8 +570,8 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
   const bool persistent = fast_shape(D, K) && saliency == nullptr;
   int r;
   if (persistent)
-    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, st)
-                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, st);
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, st);
   else
     r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
                           : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);

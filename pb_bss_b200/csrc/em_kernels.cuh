@@ -889,7 +889,7 @@ __global__ void normalize_kernel(const CT* __restrict__ y, CT* __restrict__ z, i
 // stage (ROWS rows x SF frames) is one contiguous block.  One CTA per (frame tile, bin).
 template <typename CT>
 __global__ void normalize_staged_kernel(const CT* __restrict__ y, CT* __restrict__ z, int F, int T, int D, int rows,
-                                        int SF, int nchunks) {
+                                        int SF, int nchunks, int* __restrict__ dead) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);  // [blockDim.x][D + 1]
   const int f = blockIdx.y;
@@ -909,6 +909,9 @@ __global__ void normalize_staged_kernel(const CT* __restrict__ y, CT* __restrict
       n2 += v.x * v.x + v.y * v.y;
     }
     double nrm = sqrt(n2);
+    // bins with an all-zero frame keep the reference's eigenvalue normalisation in every
+    // iteration (see em_persistent.cuh): remember them
+    if (nrm == 0.0 && dead != nullptr) dead[f] = 1;
     if (nrm == 0.0) nrm = kTiny;
     nrm = fmax(nrm, kTiny);
     for (int d = 0; d < D; ++d) {

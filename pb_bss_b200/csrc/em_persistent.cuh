@@ -64,6 +64,7 @@ struct PersistArgs {
   double* part;  // (F, K, NS + 1) raw scatter sums of the last iteration
   int* flags;    // (F) number of model updates published for the bin
   int* ticket;   // (1)
+  const int* dead;  // (F) bin has an all-zero observation frame (set by normalize_staged_kernel)
   int* status;
   CwSpline spline;  // complex Watson only: inverse hypergeometric ratio (model_kind 1)
   unsigned long long* phase;  // debug: per-phase cycle sums (PBB_PHASE_TIMING builds)
@@ -840,7 +841,9 @@ em_persistent_kernel(const PersistArgs a) {
         double tr = 0.0;
         for (int d = lane; d < D; d += 32) tr += A[d * D + d].x;
         tr = warp_sum(tr);
-        const double tn = (double)D / fmax(tr, kTiny);
+        // covariance_norm=False keeps the reference's absolute scale (it survives into the returned
+        // eigenvalues); otherwise the scale is free and tr = D keeps all classes comparable
+        const double tn = a.covariance_norm == PBB_NORM_NONE ? 1.0 : (double)D / fmax(tr, kTiny);
         for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
         __syncwarp();
         bool ok;
@@ -849,8 +852,12 @@ em_persistent_kernel(const PersistArgs a) {
         double tinv = 0.0;
         for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
         tinv = warp_sum(tinv);
-        // lambda_min / lambda_max >= 1 / (tr(A) tr(A^-1)) = 1 / (D tinv)
-        const bool no_floor = ok && isfinite(tinv) && ((double)D * tinv * a.eigenvalue_floor < 0.5);
+        // lambda_min / lambda_max >= 1 / (tr(A) tr(A^-1))
+        // A bin with an all-zero frame must keep the reference's own normalisation: such a frame has
+        // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
+        // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
+        const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
+                              (a.dead == nullptr || a.dead[bin] == 0);
         double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
         if (__any_sync(0xffffffffu, bad)) {
           if (lane == 0) atomicMax(a.status, bin + 1);

@@ -1,0 +1,15 @@
+"""Small fits for compute-sanitizer (memcheck / racecheck): lean + full persistent variants, CWMM, generic."""
+import sys
+import numpy as np
+sys.path.insert(0, '.')
+from oracle import synth
+from pb_bss_b200.distribution import CACGMMTrainer, CWMMTrainer
+y, _ = synth.structured_stft(12, 300, 8, 3, seed=1); init = synth.init_affiliation(12, 3, 300)
+m = CACGMMTrainer().fit(y, initialization=init, iterations=4); m.predict(y)
+sal = np.random.RandomState(0).uniform(0.2, 1, size=(12, 300))
+CACGMMTrainer().fit(y, initialization=init, iterations=3, saliency=sal)
+y6, _ = synth.structured_stft(7, 260, 6, 4, seed=2); i6 = synth.init_affiliation(7, 4, 260)
+CWMMTrainer().fit(y6, initialization=i6, iterations=3)
+y3, _ = synth.structured_stft(3, 70, 3, 2, seed=3); i3 = synth.init_affiliation(3, 2, 70)
+CACGMMTrainer().fit(y3, initialization=i3, iterations=3)
+print('ok')

@@ -234,6 +234,66 @@ def test_rank_deficient_observation_takes_the_floor_path():
     np.testing.assert_allclose(m.predict(y), O.cacgmm_predict(y, ref), atol=1e-4)
 
 
+@pytest.mark.parametrize('D,K', [(8, 3), (4, 2), (6, 4)])
+@pytest.mark.parametrize('variant', ['saliency', 'mask', 'trace', 'nonorm', 'w2', 'eps0', 'warm', 'floor0'])
+def test_persistent_full_variant_options(D, K, variant):
+    """Options on the template shapes (D in {4,6,8}) run through the FULL variant of the
+    persistent kernel (saliency / activity mask / log-domain softmax / user model)."""
+    from pb_bss_b200.distribution import CACGMM, CACGMMTrainer
+    from pb_bss_b200.distribution import ComplexAngularCentralGaussian as CACG
+    F, T, I = 5, 200, 6
+    y, _ = synth.structured_stft(F, T, D, K, seed=D * K)
+    init = synth.init_affiliation(F, K, T, seed=1)
+    rng = np.random.RandomState(D)
+    kw = {}
+    if variant == 'saliency':
+        kw['saliency'] = rng.uniform(0.1, 1.0, size=(F, T))
+    elif variant == 'mask':
+        sam = rng.uniform(size=(F, K, T)) > 0.25
+        sam[:, 0, :] |= ~sam.any(axis=1)
+        kw['source_activity_mask'] = sam
+    elif variant == 'trace':
+        kw['covariance_norm'] = 'trace'
+    elif variant == 'nonorm':
+        kw['covariance_norm'] = False
+    elif variant == 'w2':
+        kw['weight_constant_axis'] = -2
+    elif variant == 'eps0':
+        kw.update(affiliation_eps=0., eigenvalue_floor=1e-6)
+    elif variant == 'floor0':
+        kw.update(eigenvalue_floor=0.)
+    if variant == 'warm':
+        m0 = O.cacgmm_fit(y, init, 2)
+        ref = O.cacgmm_fit(y, m0, I)
+        start = CACGMM(weight=m0['weight'], cacg=CACG(covariance_eigenvectors=m0['eigenvectors'],
+                                                       covariance_eigenvalues=m0['eigenvalues']))
+        model = CACGMMTrainer().fit(y, initialization=start, iterations=I)
+    else:
+        ref = O.cacgmm_fit(y, init, I, **kw)
+        model = CACGMMTrainer().fit(y, initialization=init, iterations=I, **kw)
+    np.testing.assert_allclose(model.weight, ref['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.cacg.covariance_eigenvalues, ref['eigenvalues'], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(_cov(model), O.cacg_covariance_from_eig(ref['eigenvectors'], ref['eigenvalues']),
+                               rtol=1e-5, atol=1e-9)
+
+
+def test_zero_observation_frames():
+    """All-zero STFT frames (digital silence): the reference floors their quadratic form at
+    `tiny` (cacg.py:198), i.e. every class sees the same q; they still count in the weights."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    F, T, D, K, I = 6, 160, 8, 3, 6
+    y, _ = synth.structured_stft(F, T, D, K, seed=31)
+    y[:, 10:14] = 0
+    y[2, 100:131] = 0
+    init = synth.init_affiliation(F, K, T, seed=2)
+    ref = O.cacgmm_fit(y, init, I)
+    model = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+    np.testing.assert_allclose(model.weight, ref['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), O.cacg_covariance_from_eig(ref['eigenvectors'], ref['eigenvalues']),
+                               rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(model.predict(y), O.cacgmm_predict(y, ref), rtol=1e-6, atol=1e-9)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
