@@ -223,6 +223,15 @@ int pbb_souden(const void* phi, const void* target_psd, const void* noise_psd,
 int pbb_blind_analytic_normalization(const void* vector, const void* noise_psd,
                                      int n, int D, void* out, void* stream);
 
+/* Rank-1 PSD approximation a a^H * trace(cov) / trace(a a^H)
+ * (get_pca_rank_one_estimate / get_gev_rank_one_estimate, beamformer_wrapper.py:11-69). */
+int pbb_rank_one_estimate(const void* vector, const void* covariance, int n,
+                          int D, void* out, void* stream);
+
+/* out = matrix @ vector per batch entry (the scaled GEV ATF Phi_nn w, beamformer_wrapper.py:27-46). */
+int pbb_matvec_batched(const void* matrix, const void* vector, int n, int D,
+                       void* out, void* stream);
+
 /* apply_beamforming_vector (beamformer.py:572-583): out[f][t] = sum_d conj(w[f][d]) mix[f][d][t]. */
 int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
                                  int F, int D, int T, void* out, void* stream);

@@ -199,6 +199,22 @@ def make_beamformer(ref):
         souden=souden, ref_channel=ref_ch, ban=ban, applied=applied)
 
 
+def make_bf_wrapper(ref):
+    import importlib
+    bw = importlib.import_module('pb_bss.extraction.beamformer_wrapper')
+    g = np.load(os.path.join(OUT, 'beamformer.npz'))
+    target, noise = g['target'], g['noise']
+    out = dict(target=target, noise=noise)
+    names = ['pca', 'pca+mvdr', 'scaled_gev_atf+mvdr', 'mvdr_souden', 'mvdr_souden+ban',
+             'rank1_pca+mvdr_souden', 'rank1_gev+mvdr_souden+ban', 'gev', 'gev+ban',
+             'rank1_pca+gev', 'ch1']
+    for n in names:
+        out['bf_' + n] = np.asarray(bw.get_bf_vector(n, target.copy(), noise.copy()))
+    out['rank1_pca'] = bw.get_pca_rank_one_estimate(target.copy())
+    out['rank1_gev'] = bw.get_gev_rank_one_estimate(target.copy(), noise.copy())
+    np.savez_compressed(os.path.join(OUT, 'bf_wrapper.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -207,6 +223,7 @@ def main():
     make_cwmm(ref)
     make_permutation(ref)
     make_beamformer(ref)
+    make_bf_wrapper(ref)
     total = 0
     for n in sorted(os.listdir(OUT)):
         s = os.path.getsize(os.path.join(OUT, n))

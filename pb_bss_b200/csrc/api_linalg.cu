@@ -192,6 +192,32 @@ int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
   return 0;
 }
 
+int pbb_rank_one_estimate(const void* vector, const void* covariance, int n, int D, void* out, void* stream) {
+  PBB_CHECK_ARG(vector && covariance, 1, "input is null");
+  PBB_CHECK_ARG(n > 0 && D > 0 && D <= 64, 3, "bad shape");
+  PBB_CHECK_ARG(out != nullptr, 5, "out is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("rank_one_kernel", st);
+  rank_one_kernel<<<n, 64, 0, st>>>(reinterpret_cast<const double2*>(vector),
+                                    reinterpret_cast<const double2*>(covariance), n, D,
+                                    reinterpret_cast<double2*>(out));
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pbb_matvec_batched(const void* matrix, const void* vector, int n, int D, void* out, void* stream) {
+  PBB_CHECK_ARG(matrix && vector, 1, "input is null");
+  PBB_CHECK_ARG(n > 0 && D > 0 && D <= 64, 3, "bad shape");
+  PBB_CHECK_ARG(out != nullptr, 5, "out is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("matvec_kernel", st);
+  matvec_kernel<<<(n + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double2*>(matrix),
+                                                 reinterpret_cast<const double2*>(vector), n, D,
+                                                 reinterpret_cast<double2*>(out));
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 size_t pbb_psd_workspace_bytes(int F, int T, int D, int K) {
   if (F <= 0 || T <= 0 || D <= 0 || K <= 0) return 0;
   return (size_t)F * ((T + 31) / 32) * K * ((size_t)D * D + 1) * sizeof(double) + 256;

@@ -319,6 +319,42 @@ __global__ void apply_bf_kernel(const double2* __restrict__ w, const CT* __restr
   out[(size_t)f * T + t] = s;
 }
 
+// ---- rank-1 PSD approximations (beamformer_wrapper.py:11-69) ---------------------
+// out = a a^H * trace(cov) / trace(a a^H)
+__global__ void rank_one_kernel(const double2* __restrict__ a, const double2* __restrict__ cov, int n, int D,
+                                double2* __restrict__ out) {
+  const int m = blockIdx.x;
+  if (m >= n) return;
+  const double2* __restrict__ am = a + (size_t)m * D;
+  double2 tr = make_double2(0.0, 0.0);
+  double na = 0.0;
+  for (int d = 0; d < D; ++d) {
+    const double2 c = cov[(size_t)m * D * D + d * D + d];
+    tr.x += c.x; tr.y += c.y;
+    na += am[d].x * am[d].x + am[d].y * am[d].y;
+  }
+  const double2 scale = make_double2(tr.x / na, tr.y / na);
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    const int d = i / D, e = i - d * D;
+    out[(size_t)m * D * D + i] = cmul(scale, cmulc(am[d], am[e]));
+  }
+}
+
+// y = M x per matrix (the "scaled GEV ATF" Phi_nn w, beamformer_wrapper.py:27-46)
+__global__ void matvec_kernel(const double2* __restrict__ M, const double2* __restrict__ x, int n, int D,
+                              double2* __restrict__ y) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  for (int d = 0; d < D; ++d) {
+    double2 s = make_double2(0.0, 0.0);
+    for (int e = 0; e < D; ++e) {
+      const double2 p = cmul(M[(size_t)m * D * D + d * D + e], x[(size_t)m * D + e]);
+      s.x += p.x; s.y += p.y;
+    }
+    y[(size_t)m * D + d] = s;
+  }
+}
+
 // ---- PSD assembly from the slot sums of the M-step kernels (beamformer.py:59-160) ----
 // part (F, NCH, K, NS + 1) -> psd (F, K, D, D); scale: 0 = none, 1 = 1 / max(sum mask, 1e-10)
 // (beamformer.py:127-131), 2 = 1 / T (no mask, beamformer.py:114-117)

@@ -9,3 +9,4 @@ from .beamformer import (  # noqa: F401
     get_pca_vector,
     get_power_spectral_density_matrix,
 )
+from .beamformer_wrapper import get_bf_vector  # noqa: F401

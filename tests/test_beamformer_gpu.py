@@ -110,3 +110,34 @@ def test_mvdr_distortionless_and_broadcast():
     assert w.shape == (2, F, D)
     np.testing.assert_allclose(np.einsum('kfd,kfd->kf', w.conj(), atf), 1, atol=1e-10)
     np.testing.assert_allclose(w, O.mvdr_vector(atf, noise), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize('name,phase_free', [
+    ('pca', True), ('pca+mvdr', True), ('scaled_gev_atf+mvdr', True), ('mvdr_souden', False),
+    ('mvdr_souden+ban', False), ('rank1_pca+mvdr_souden', False), ('rank1_gev+mvdr_souden+ban', False),
+    ('gev', True), ('gev+ban', True), ('rank1_pca+gev', True), ('ch1', False)])
+def test_get_bf_vector_matches_reference_golden(name, phase_free):
+    """String dispatcher of pb_bss/extraction/beamformer_wrapper.py:117-236."""
+    from pb_bss_b200.extraction import get_bf_vector
+    g = load_golden('bf_wrapper')
+    w = get_bf_vector(name, g['target'], g['noise'])
+    ref = g['bf_' + name]
+    assert w.shape == ref.shape
+    if phase_free:  # eigenvector based: arbitrary phase per bin
+        np.testing.assert_allclose(cos_similarity(w, ref), 1, atol=1e-9)
+        np.testing.assert_allclose(np.linalg.norm(w, axis=-1), np.linalg.norm(ref, axis=-1), rtol=1e-8)
+    else:
+        np.testing.assert_allclose(w, ref, rtol=1e-8, atol=1e-11)
+
+
+def test_rank_one_estimates_match_reference_golden():
+    from pb_bss_b200.extraction.beamformer_wrapper import get_gev_rank_one_estimate, get_pca_rank_one_estimate
+    g = load_golden('bf_wrapper')
+    np.testing.assert_allclose(get_pca_rank_one_estimate(g['target']), g['rank1_pca'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(get_gev_rank_one_estimate(g['target'], g['noise']), g['rank1_gev'], rtol=1e-8, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        from pb_bss_b200.extraction import get_bf_vector
+        get_bf_vector('wmwf', g['target'], g['noise'])
+    with pytest.raises(ValueError):
+        from pb_bss_b200.extraction import get_bf_vector
+        get_bf_vector('nonsense', g['target'], g['noise'])
