@@ -119,7 +119,7 @@ def _cpu_fit_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline_single(iters=20):
+def cpu_baseline_single(iters=40):
     """As shipped: one process (the hot einsums are single threaded)."""
     from oracle import pb_bss_oracle as O
     y, init = _inputs(0)
