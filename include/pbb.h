@@ -46,6 +46,8 @@ extern "C" {
 /* weight_constant_axis (pb_bss/distribution/mixture_model_utils.py:133-203) */
 #define PBB_WEIGHT_TIME 0     /* (-1,): one weight per (bin, class) */
 #define PBB_WEIGHT_CONST 1    /* -2: constant 1/K */
+#define PBB_WEIGHT_TIED_TIME 2 /* (-3,): frequency-tied weights, one per (class, frame): array (K, T) */
+#define PBB_WEIGHT_TIED 3     /* (-3, -1): frequency-tied, one per class: array (K) */
 
 const char* pbb_last_error(void);
 int pbb_version(void);
@@ -116,6 +118,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K,
  *  quadratic    (F, K, T) float64 out (may be NULL)
  *  loglik       (F) float64 out, per-bin sum_t logsumexp_k log_pdf (may be NULL)
  *  affiliation_eps: 0 for predict (cacgmm.py:73)
+ *  weight / weight_mode: (F, K) for PBB_WEIGHT_TIME, ignored for _CONST, (K, T) for
+ *  _TIED_TIME and (K) for _TIED (frequency-tied weights, mixture_model_utils.py:187-190)
  */
 int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K,
                        const void* eigenvectors, const double* eigenvalues,
@@ -136,6 +140,13 @@ int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K,
                      void* eigenvectors, double* eigenvalues, double* weight,
                      void* workspace, size_t workspace_bytes, int* status,
                      void* stream);
+
+/* estimate_mixture_weight with weight_constant_axis=(-3,) / (-3, -1)
+ * (mixture_model_utils.py:133-203, no saliency): weight_kt[k][t] = mean over bins of
+ * affiliation[f][k][t]; with also_over_time additionally weight_k[k] = mean over t. */
+int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T,
+                                 int also_over_time, double* weight_kt,
+                                 double* weight_k, void* stream);
 
 /* ------------------------------------------------------------------------
  * Complex Watson mixture model (pb_bss/distribution/cwmm.py, complex_watson.py).

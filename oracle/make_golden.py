@@ -82,6 +82,25 @@ def make_cacgmm(ref):
         l5=m5.cacg.covariance_eigenvalues)
 
 
+def make_cacgmm_coupled(ref):
+    """Frequency-tied weights and inline permutation alignment (cacgmm.py:252-278)."""
+    pa = ref.permutation_alignment
+    y, _ = synth.structured_stft(65, 60, 4, 2, seed=21)
+    init = synth.init_affiliation(65, 2, 60, seed=5)
+    _cacgmm_case(ref, 'cacgmm_tied_time', y, init, 5, weight_constant_axis=(-3,))
+    _cacgmm_case(ref, 'cacgmm_tied', y, init, 5, weight_constant_axis=(-3, -1))
+    al = pa.DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+                                     main_iterations=5, sub_iterations=2)
+    T = ref.distribution.CACGMMTrainer
+    model = T().fit(y, initialization=init, iterations=5, weight_constant_axis=(-3,),
+                    inline_permutation_aligner=al)
+    np.savez_compressed(
+        os.path.join(OUT, 'cacgmm_inline_pa.npz'), y=y, init=init, iterations=5,
+        plan=np.asarray(al.alignment_plan), weight=model.weight,
+        eigenvalues=model.cacg.covariance_eigenvalues, covariance=model.cacg.covariance,
+        affiliation=model.predict(y))
+
+
 def make_cacg_steps(ref):
     """Single E / M step pieces on fixed model parameters."""
     rng = np.random.RandomState(21)
@@ -219,6 +238,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
     make_cacgmm(ref)
+    make_cacgmm_coupled(ref)
     make_cacg_steps(ref)
     make_cwmm(ref)
     make_permutation(ref)

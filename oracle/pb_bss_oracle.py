@@ -183,13 +183,16 @@ def cacgmm_m_step(z, quadratic_form, affiliation, saliency=None,
 def cacgmm_fit(y, initialization, iterations=100, *, saliency=None,
                source_activity_mask=None, weight_constant_axis=(-1,),
                hermitize=True, covariance_norm='eigenvalue',
-               affiliation_eps=1e-10, eigenvalue_floor=1e-10):
+               affiliation_eps=1e-10, eigenvalue_floor=1e-10,
+               inline_permutation_plan=None):
     """EM loop of ``CACGMMTrainer.fit`` (pb_bss/distribution/cacgmm.py:142-280).
 
     ``initialization`` is an affiliation array (..., K, N) (singleton
     independent dims broadcast, cacgmm.py:211-228) or a model dict
     (warm start, cacgmm.py:229-234).  Random initialisation (cacgmm.py:206-210)
     is the caller's job: draw ``np.random.uniform`` and normalise over K.
+    ``inline_permutation_plan``: alignment plan of a DHTVPermutationAlignment run
+    after every E-step (``inline_permutation_aligner``, cacgmm.py:260-267).
     Returns dict(weight, eigenvectors, eigenvalues).
     """
     assert np.iscomplexobj(y), y.dtype
@@ -210,6 +213,15 @@ def cacgmm_fit(y, initialization, iterations=100, *, saliency=None,
         if model is not None:
             affiliation, quadratic_form, _lp = cacgmm_e_step(
                 z, model, source_activity_mask, affiliation_eps)
+            if inline_permutation_plan is not None:
+                # apply_inline_permutation_alignment, mixture_model_utils.py:264-306
+                # (cacgmm.py:260-267): DHTV alignment of the (K, F, T) affiliations,
+                # the quadratic forms follow the same mapping
+                mask = np.ascontiguousarray(np.transpose(affiliation, (1, 0, 2)))
+                mapping = dhtv_calculate_mapping(mask, inline_permutation_plan)
+                affiliation = np.transpose(apply_mapping(mask, mapping), (1, 0, 2))
+                quadratic_form = np.transpose(
+                    apply_mapping(np.transpose(quadratic_form, (1, 0, 2)), mapping), (1, 0, 2))
         model = cacgmm_m_step(
             z, quadratic_form, affiliation, saliency, hermitize,
             covariance_norm, eigenvalue_floor, weight_constant_axis)

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('PBB_LIB') or os.path.join(_HERE, 'libpbb.so')
 
 PBB_C64, PBB_C128 = 0, 1
 NORM_NONE, NORM_EIGENVALUE, NORM_TRACE = 0, 1, 2
-WEIGHT_TIME, WEIGHT_CONST = 0, 1
+WEIGHT_TIME, WEIGHT_CONST, WEIGHT_TIED_TIME, WEIGHT_TIED = 0, 1, 2, 3
 
 
 class CacgmmOptions(ctypes.Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
     'pbb_cacgmm_mstep': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                               ctypes.POINTER(CacgmmOptions), _vp, _vp, _vp,
                               _vp, _sz, _vp, _vp]),
+    'pbb_mixture_weight_over_bins': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     'pbb_cwmm_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'pbb_cwmm_fit': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _d,
                           _vp, _vp, _vp, _vp, _sz, _vp, _vp]),

@@ -37,6 +37,30 @@ __global__ void sum_rows_kernel(const double* in, double* out, int rows, int n) 
   out[r] = s;
 }
 
+// out[k][t] = mean over f of aff[f][k][t]   (estimate_mixture_weight, axis -3)
+__global__ void mean_over_bins_kernel(const double* __restrict__ aff, int F, int K, int T, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * T) return;
+  double s = 0.0;
+  for (int f = 0; f < F; ++f) s += aff[(size_t)f * K * T + i];
+  out[i] = s / (double)F;
+}
+// out[k] = mean over t of in[k][t]
+__global__ void mean_over_time_kernel(const double* __restrict__ in, int K, int T, double* __restrict__ out) {
+  const int k = blockIdx.x;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) s += in[(size_t)k * T + t];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    out[k] = tot / (double)T;
+  }
+}
+
 // ---- workspace carving -------------------------------------------------------
 struct CacgmmWorkspace {
   void* z;
@@ -473,6 +497,7 @@ int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K, con
   if (int r = check_shape(F, T, D, K, dtype)) return r;
   PBB_CHECK_ARG(eigenvectors && eigenvalues, 7, "model is null");
   PBB_CHECK_ARG(weight != nullptr || weight_mode == PBB_WEIGHT_CONST, 9, "weight is null");
+  PBB_CHECK_ARG(weight_mode >= 0 && weight_mode <= PBB_WEIGHT_TIED, 10, "bad weight_mode");
   PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 16,
                 "workspace too small (pbb_cacgmm_workspace_bytes)");
   PBB_CHECK_ARG(status != nullptr, 18, "status is null");
@@ -486,13 +511,15 @@ int pbb_cacgmm_predict(const void* y, int dtype, int F, int T, int D, int K, con
   fe.F = F; fe.D = D; fe.K = K;
   fe.evec = reinterpret_cast<const double2*>(eigenvectors);
   fe.eval = eigenvalues;
-  fe.weight = weight_mode == PBB_WEIGHT_CONST ? nullptr : weight;
+  const bool tied = weight_mode == PBB_WEIGHT_TIED_TIME || weight_mode == PBB_WEIGHT_TIED;
+  fe.weight = (weight_mode == PBB_WEIGHT_CONST || tied) ? nullptr : weight;
   fe.coef = ws.coef; fe.ld = ws.ld; fe.w = ws.w; fe.ew = ws.ew;
   if ((r = launch_from_eig(fe, st))) return r;
   EmArgs a;
   memset(&a, 0, sizeof(a));
   a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
   a.mode = kModeE; a.softmax_fast = 0;
+  if (tied) { a.w_time = weight; a.w_time_st = weight_mode == PBB_WEIGHT_TIED_TIME ? 1 : 0; }
   a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
   a.activity = activity; a.aff_eps = affiliation_eps;
   a.aff_out = affiliation; a.q_out = quadratic;
@@ -659,6 +686,20 @@ int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K, const
   a.aff_out = affiliation;
   int nch = launch_em(a, dtype, 0, st);
   return nch > 0 ? 0 : (nch ? nch : 1);
+}
+
+int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T, int also_over_time, double* weight_kt,
+                                 double* weight_k, void* stream) {
+  PBB_CHECK_ARG(affiliation != nullptr, 1, "affiliation is null");
+  PBB_CHECK_ARG(F > 0 && K > 0 && T > 0, 2, "bad shape");
+  PBB_CHECK_ARG(weight_kt != nullptr, 6, "weight (K, T) output is null");
+  PBB_CHECK_ARG(!also_over_time || weight_k != nullptr, 7, "weight (K) output is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("mean_over_bins_kernel", st);
+  mean_over_bins_kernel<<<(K * T + 255) / 256, 256, 0, st>>>(affiliation, F, K, T, weight_kt);
+  if (also_over_time) mean_over_time_kernel<<<K, 256, 0, st>>>(weight_kt, K, T, weight_k);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -19,6 +19,8 @@ struct EmArgs {
   const double* ld;
   const double* w;
   const double* ew;
+  const double* w_time;     // frequency-tied weights (K, T) [w_time_st = 1] or (K) [w_time_st = 0], or null
+  int w_time_st;
   const uint8_t* activity;  // (F, K, T) or null
   double aff_eps;
   const double* aff_in;    // (F, K, T), mode M

@@ -211,6 +211,13 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
 #pragma unroll
         for (int k = 0; k < K; ++k) invq[k] = 1.0;
         ll = 0.0;
+      } else if (a.w_time != nullptr) {
+        // frequency-tied mixture weights (weight_constant_axis=-3, mixture_model_utils.py:187-190):
+        // one weight per (class, frame) shared by all bins; log-domain softmax
+        double wl[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) wl[k] = a.w_time[(size_t)k * (a.w_time_st ? T : 1) + (a.w_time_st && valid ? t : 0)];
+        em_softmax<D, K>(q, sm.ld, wl, sm.ew, act, (size_t)T, false, a.aff_eps, want_ll, gam, invq, ll);
       } else {
         em_softmax<D, K>(q, sm.ld, sm.w, sm.ew, act, (size_t)T, fast, a.aff_eps, want_ll, gam, invq, ll);
       }
@@ -366,7 +373,9 @@ __global__ void __launch_bounds__(kGenFrames) em_generic_kernel(const EmArgs a) 
     for (int k = 0; k < K; ++k) {
       const double e = exp(lp[k] - m);
       se += e;
-      double av = e * a.w[(size_t)f * K + k];
+      const double wk = a.w_time ? a.w_time[(size_t)k * (a.w_time_st ? T : 1) + (a.w_time_st && valid ? t : 0)]
+                                : a.w[(size_t)f * K + k];
+      double av = e * wk;
       if (a.activity && valid) av = a.activity[((size_t)f * K + k) * T + t] ? av : 0.0;
       gam[k] = av;
       den += av;

@@ -27,7 +27,9 @@ _NORMS = {'eigenvalue': _lib.NORM_EIGENVALUE, 'trace': _lib.NORM_TRACE,
 
 def _weight_mode(weight_constant_axis, ndim):
     """Maps ``weight_constant_axis`` (mixture_model_utils.py:133-203) onto the
-    modes the kernels implement; ``ndim`` is the affiliation rank."""
+    modes the kernels implement; ``ndim`` is the affiliation rank.
+    WEIGHT_TIME: (-1,); WEIGHT_CONST: -2; WEIGHT_TIED_TIME: (-3,) and
+    WEIGHT_TIED: (-3, -1) (frequency-tied, only for a single independent dim)."""
     if isinstance(weight_constant_axis, list):
         weight_constant_axis = tuple(weight_constant_axis)
     if isinstance(weight_constant_axis, int):
@@ -36,13 +38,16 @@ def _weight_mode(weight_constant_axis, ndim):
             return _lib.WEIGHT_CONST  # constant 1/K, shape (K, 1)
         axes = (ax,)
     else:
-        axes = tuple(a % ndim - ndim for a in weight_constant_axis)
+        axes = tuple(sorted(a % ndim - ndim for a in weight_constant_axis))
     if axes == (-1,):
         return _lib.WEIGHT_TIME
+    if ndim == 3 and axes == (-3,):
+        return _lib.WEIGHT_TIED_TIME
+    if ndim == 3 and axes == (-3, -1):
+        return _lib.WEIGHT_TIED
     raise NotImplementedError(
-        f'weight_constant_axis={weight_constant_axis!r}: only (-1,) and -2 run '
-        'on the device so far; frequency-tied weights couple the bins '
-        '(SURVEY.md section 8f, rank 2).')
+        f'weight_constant_axis={weight_constant_axis!r}: supported on the '
+        'device are (-1,), -2 and, for (F, K, T) affiliations, (-3,) / (-3, -1).')
 
 
 def _flatten_obs(y):
@@ -73,11 +78,12 @@ class CACGMM(_ProbabilisticModel):
         V = V.expand(*independent, K, D, D).reshape(F, K, D, D).contiguous()
         lam = lam.expand(*independent, K, D).reshape(F, K, D).contiguous()
         w = _device.to_device(self.weight, torch.float64)
-        assert w.shape[-1] == 1, (
-            'time-varying weights (weight_constant_axis=-3) are not supported '
-            'on the device yet', tuple(w.shape))
+        if w.shape[-1] != 1:
+            # frequency-tied, time-varying weights (1, K, T) of weight_constant_axis=(-3,)
+            assert w.dim() == 3 and w.shape[0] == 1 and len(independent) == 1, tuple(w.shape)
+            return V, lam, w[0].contiguous(), K, _lib.WEIGHT_TIED_TIME
         w = w[..., 0].expand(*independent, K).reshape(F, K).contiguous()
-        return V, lam, w, K
+        return V, lam, w, K, _lib.WEIGHT_TIME
 
     def _run_predict(self, y, source_activity_mask, affiliation_eps,
                      want_aff=True, want_q=False, want_ll=False):
@@ -85,7 +91,7 @@ class CACGMM(_ProbabilisticModel):
         yd = _device.to_device(y)
         code = _device.complex_dtype_code(yd)
         independent, F, N, D = _flatten_obs(yd)
-        V, lam, w, K = self._device_model(independent, F)
+        V, lam, w, K, wmode = self._device_model(independent, F)
         assert V.shape[-1] == D, (V.shape, D)
         act = None
         if source_activity_mask is not None:
@@ -101,7 +107,7 @@ class CACGMM(_ProbabilisticModel):
         ws = _device.workspace(nbytes)
         _lib.check(lib.pbb_cacgmm_predict(
             _device.ptr(yd), code, F, N, D, K, _device.ptr(V), _device.ptr(lam),
-            _device.ptr(w), _lib.WEIGHT_TIME, _device.ptr(act),
+            _device.ptr(w), wmode, _device.ptr(act),
             float(affiliation_eps), _device.ptr(aff), _device.ptr(q),
             _device.ptr(ll), _device.ptr(ws), nbytes, _device.ptr(status),
             _device.stream_ptr()), 'pbb_cacgmm_predict')
@@ -168,10 +174,6 @@ class CACGMMTrainer:
             'Incompatible input combination. '
             'Exactly one of the two inputs has to be None: '
             f'{initialization is None} xor {num_classes is None}')
-        if inline_permutation_aligner is not None:
-            raise NotImplementedError(
-                'inline_permutation_aligner couples the bins inside the EM '
-                'loop (SURVEY.md section 8f, rank 2); not on the device yet.')
         assert covariance_norm in _NORMS, covariance_norm
         like_numpy = not _device.is_tensor(y)
         yd = _device.to_device(y)
@@ -205,6 +207,13 @@ class CACGMMTrainer:
             raise TypeError('No sufficient initialization.')
         assert K < 20, f'num_classes: {K}, sure?'
         weight_mode = _weight_mode(weight_constant_axis, len(independent) + 2)
+        if inline_permutation_aligner is not None or weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED):
+            # frequency-tied weights and the inline permutation alignment couple the bins inside the
+            # EM loop (cacgmm.py:252-278): one E-step / alignment / M-step round trip per iteration
+            return self._fit_coupled(
+                yd, like_numpy, init_dev, model_in, K, iterations, saliency, source_activity_mask,
+                weight_mode, hermitize, covariance_norm, affiliation_eps, eigenvalue_floor,
+                inline_permutation_aligner, weight_constant_axis)
 
         act = None
         if source_activity_mask is not None:
@@ -221,7 +230,8 @@ class CACGMMTrainer:
             sal = sal.expand(*independent, N).reshape(F, N).contiguous()
 
         if model_in is not None:
-            V, lam, w, _ = model_in._device_model(independent, F)
+            V, lam, w, _, wm_in = model_in._device_model(independent, F)
+            assert wm_in == _lib.WEIGHT_TIME, 'warm start with frequency-tied weights goes through the coupled loop'
             V, lam, w = V.clone(), lam.clone(), w.clone()
         else:
             V = _device.empty((F, K, D, D), torch.complex128)
@@ -258,6 +268,59 @@ class CACGMMTrainer:
                     V.reshape(*independent, K, D, D), like_numpy),
                 covariance_eigenvalues=_device.to_host(
                     lam.reshape(*independent, K, D), like_numpy)))
+
+    def _fit_coupled(self, yd, like_numpy, init_dev, model_in, K, iterations, saliency, source_activity_mask,
+                     weight_mode, hermitize, covariance_norm, affiliation_eps, eigenvalue_floor, aligner,
+                     weight_constant_axis):
+        """EM with per-iteration coupling across bins: frequency-tied mixture weights
+        (``weight_constant_axis`` (-3,) / (-3, -1), mixture_model_utils.py:187-190) and / or the
+        inline permutation alignment (mixture_model_utils.py:264-306).  Every step runs on the
+        device; the loop itself is the reference's (cacgmm.py:252-278)."""
+        from ..permutation_alignment import apply_mapping
+        independent, F, N, D = _flatten_obs(yd)
+        tied = weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED)
+        if aligner is not None:
+            message = ('Inline permutation alignment reduces mismatch between frequency independent '
+                       'mixtures weights and a frequency independent observation model. Therefore, we '
+                       f'require `affiliation.ndim == 3` and a corresponding `weight_constant_axis` '
+                       f'({weight_constant_axis}).')
+            assert len(independent) == 1 and tied, message
+        if tied and saliency is not None:
+            raise NotImplementedError('saliency together with frequency-tied weights is not on the device yet')
+        lib = _lib.load()
+        model = model_in
+        affiliation = init_dev.reshape(*independent, K, N) if init_dev is not None else None
+        quadratic_form = None
+        m_axis = (-1,) if tied else weight_constant_axis
+        for _ in range(iterations):
+            if model is not None:
+                affiliation, quadratic_form, _, _ = model._run_predict(
+                    yd, source_activity_mask, affiliation_eps, want_q=True)
+                if aligner is not None:
+                    mask_kft = affiliation.permute(1, 0, 2).contiguous()
+                    mapping = aligner.calculate_mapping(mask_kft)
+                    affiliation = apply_mapping(mask_kft, mapping).permute(1, 0, 2).contiguous()
+                    quadratic_form = apply_mapping(quadratic_form.permute(1, 0, 2).contiguous(),
+                                                   mapping).permute(1, 0, 2).contiguous()
+            model = cacgmm_m_step(
+                yd, quadratic_form, affiliation, saliency=saliency, hermitize=hermitize,
+                covariance_norm=covariance_norm, eigenvalue_floor=eigenvalue_floor,
+                weight_constant_axis=m_axis)
+            if tied:
+                aff = affiliation.reshape(F, K, N).contiguous()
+                w_kt = _device.empty((K, N), torch.float64)
+                w_k = _device.empty((K,), torch.float64)
+                _lib.check(lib.pbb_mixture_weight_over_bins(
+                    _device.ptr(aff), F, K, N, int(weight_mode == _lib.WEIGHT_TIED), _device.ptr(w_kt),
+                    _device.ptr(w_k), _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
+                model.weight = w_kt[None] if weight_mode == _lib.WEIGHT_TIED_TIME else w_k[None, :, None]
+        if like_numpy:
+            model = CACGMM(
+                weight=_device.to_host(model.weight, True) if _device.is_tensor(model.weight) else model.weight,
+                cacg=ComplexAngularCentralGaussian(
+                    covariance_eigenvectors=_device.to_host(model.cacg.covariance_eigenvectors, True),
+                    covariance_eigenvalues=_device.to_host(model.cacg.covariance_eigenvalues, True)))
+        return model
 
     def fit_predict(self, y, initialization=None, num_classes=None,
                     iterations=100, **kwargs):

@@ -75,7 +75,10 @@ def test_weight_axis_mapping():
     assert _weight_mode(2, 3) == _lib.WEIGHT_TIME
     assert _weight_mode(-2, 3) == _lib.WEIGHT_CONST
     assert _weight_mode(1, 3) == _lib.WEIGHT_CONST
+    assert _weight_mode((-3,), 3) == _lib.WEIGHT_TIED_TIME
+    assert _weight_mode((-3, -1), 3) == _lib.WEIGHT_TIED
+    assert _weight_mode((-1, -3), 3) == _lib.WEIGHT_TIED
     with pytest.raises(NotImplementedError):
-        _weight_mode((-3,), 3)
+        _weight_mode((-3,), 4)  # more than one independent dim
     with pytest.raises(NotImplementedError):
-        _weight_mode((-3, -1), 3)
+        _weight_mode((-4, -1), 4)

@@ -294,6 +294,37 @@ def test_zero_observation_frames():
     np.testing.assert_allclose(model.predict(y), O.cacgmm_predict(y, ref), rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize('name,axis', [('cacgmm_tied_time', (-3,)), ('cacgmm_tied', (-3, -1))])
+def test_frequency_tied_weights_match_reference_golden(name, axis):
+    """weight_constant_axis (-3,) / (-3, -1): one weight per (class, frame) / per class shared by
+    all bins (mixture_model_utils.py:187-190) -- couples the bins in every iteration."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    g = load_golden(name)
+    model = CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=int(g['iterations']),
+                                weight_constant_axis=axis)
+    assert model.weight.shape == g['weight'].shape
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), g['covariance'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-6, atol=1e-9)
+
+
+def test_inline_permutation_alignment_matches_reference_golden():
+    """inline_permutation_aligner (cacgmm.py:260-267, mixture_model_utils.py:264-306)."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+    g = load_golden('cacgmm_inline_pa')
+    al = DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+                                  main_iterations=5, sub_iterations=2)
+    assert al.alignment_plan == g['plan'].tolist()
+    model = CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=5, weight_constant_axis=(-3,),
+                                inline_permutation_aligner=al)
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), g['covariance'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-6, atol=1e-9)
+    with pytest.raises(AssertionError):  # needs frequency-tied weights, like the reference
+        CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=2, inline_permutation_aligner=al)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
@@ -306,7 +337,7 @@ def test_argument_errors():
     with pytest.raises(AssertionError):
         CACGMMTrainer().fit(y, num_classes=2, iterations=0)
     with pytest.raises(NotImplementedError):
-        CACGMMTrainer().fit(y, num_classes=2, weight_constant_axis=(-3,))
+        CACGMMTrainer().fit(y.reshape(1, 2, 20, 4), num_classes=2, weight_constant_axis=(-4,))
 
 
 def test_nonfinite_input_raises():

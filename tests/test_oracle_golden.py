@@ -48,6 +48,25 @@ def test_cacgmm_fit_matches_reference(name):
                                g['log_likelihood'], rtol=1e-9)
 
 
+@pytest.mark.parametrize('name,axis', [('cacgmm_tied_time', (-3,)), ('cacgmm_tied', (-3, -1))])
+def test_cacgmm_frequency_tied_weights(name, axis):
+    g = load_golden(name)
+    m = O.cacgmm_fit(g['y'], g['init'], int(g['iterations']), weight_constant_axis=axis)
+    assert m['weight'].shape == g['weight'].shape
+    np.testing.assert_allclose(m['weight'], g['weight'], rtol=1e-9)
+    np.testing.assert_allclose(O.cacg_covariance_from_eig(m['eigenvectors'], m['eigenvalues']), g['covariance'],
+                               rtol=1e-7, atol=1e-10)
+
+
+def test_cacgmm_inline_permutation_alignment():
+    g = load_golden('cacgmm_inline_pa')
+    m = O.cacgmm_fit(g['y'], g['init'], 5, weight_constant_axis=(-3,), inline_permutation_plan=g['plan'].tolist())
+    np.testing.assert_allclose(m['weight'], g['weight'], rtol=1e-9)
+    np.testing.assert_allclose(O.cacg_covariance_from_eig(m['eigenvectors'], m['eigenvalues']), g['covariance'],
+                               rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(O.cacgmm_predict(g['y'], m), g['affiliation'], rtol=1e-7, atol=1e-10)
+
+
 def test_cacgmm_warm_start():
     g = load_golden('cacgmm_warm')
     m3 = dict(weight=g['w3'], eigenvectors=g['V3'], eigenvalues=g['l3'])
