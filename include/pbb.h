@@ -267,6 +267,32 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan,
 int pbb_apply_mapping(const double* mask, const long long* mapping, int K,
                       int F, int T, double* out, void* stream);
 
+/* _ScoreMatrix.multiply / cos / euclidean (:380-420): scores (F, K, K) with
+ * scores[f][k_reference][k_mask] over the T frames of bin f.  Source k of a
+ * side starts at base + k * source_stride (elements), its bins are T apart, so
+ * the shifted views mask[:, 1:] / mask[:, :-1] of GreedyPermutationAlignment
+ * (:702) are passed without a copy.  metric: */
+enum { PBB_SCORE_MULTIPLY = 0, PBB_SCORE_COS = 1, PBB_SCORE_EUCLIDEAN = 2 };
+int pbb_score_matrix(const double* mask, const double* reference,
+                     long long mask_source_stride,
+                     long long reference_source_stride, int K, int F, int T,
+                     int metric, double* scores, void* stream);
+
+/* _mapping_from_score_matrix (:458-590): scores (F, K, K) -> mapping (K, F)
+ * int64.  algorithm 0 = 'greedy', 1 = 'optimal' (first best of
+ * itertools.permutations).  *status = 1 + bin of a non-finite score matrix
+ * (the reference raises ValueError('score matrix is infeasible')). */
+enum { PBB_ASSIGN_GREEDY = 0, PBB_ASSIGN_OPTIMAL = 1 };
+int pbb_mapping_from_score_matrix(const double* scores, int F, int K,
+                                  int algorithm, long long* mapping,
+                                  int* status, void* stream);
+
+/* GreedyPermutationAlignment.calculate_mapping (:700-712), last step:
+ * pair_mapping (K, F-1) = mapping of every bin to its lower neighbour;
+ * mapping (K, F): column 0 identity, column f = pair[mapping[:, f-1], f-1]. */
+int pbb_chain_mapping(const long long* pair_mapping, int K, int F,
+                      long long* mapping, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

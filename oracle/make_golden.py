@@ -190,6 +190,37 @@ def make_permutation(ref):
     np.savez_compressed(os.path.join(OUT, 'permutation.npz'), **out)
 
 
+def make_permutation_greedy_oracle(ref):
+    """GreedyPermutationAlignment / OraclePermutationAlignment / _mapping_from_score_matrix
+    (permutation_alignment.py:458-786) on a permuted synthetic mask and on pure noise."""
+    pa = ref.permutation_alignment
+    rng = np.random.RandomState(32)
+    out = {}
+    K, F, T = 3, 65, 40
+    proto = rng.uniform(size=(K, 1, T)) ** 4
+    clean = proto + 0.5 * rng.uniform(size=(K, F, T))
+    clean /= clean.sum(0, keepdims=True)
+    perm = np.stack([rng.permutation(K) for _ in range(F)], axis=1)
+    out['mask'] = clean[perm, np.arange(F)]
+    out['reference_mask'] = clean
+    noise = rng.uniform(size=(4, 33, 20))
+    out['noise'] = noise / noise.sum(0, keepdims=True)
+    out['noise_reference'] = rng.uniform(size=(4, 33, 20))
+    for metric in ('cos', 'euclidean', 'multiply'):
+        out[f'greedy_{metric}'] = pa.GreedyPermutationAlignment(metric).calculate_mapping(out['mask'])
+        out[f'greedy_noise_{metric}'] = pa.GreedyPermutationAlignment(metric).calculate_mapping(out['noise'])
+        out[f'scores_{metric}'] = getattr(pa._ScoreMatrix, metric)(out['noise'], out['noise_reference'])
+        for alg in ('greedy', 'optimal'):
+            al = pa.OraclePermutationAlignment(metric, alg)
+            out[f'oracle_{metric}_{alg}'] = al.calculate_mapping(out['mask'], out['reference_mask'])
+            out[f'oracle_noise_{metric}_{alg}'] = al.calculate_mapping(out['noise'], out['noise_reference'])
+    sm = np.array([[11, 10, 0], [4, 5, 10], [6, 0, 5]])  # doctest, :475-508
+    out['score'] = sm
+    out['score_greedy'] = pa._mapping_from_score_matrix(sm, 'greedy')
+    out['score_optimal'] = pa._mapping_from_score_matrix(sm, 'optimal')
+    np.savez_compressed(os.path.join(OUT, 'permutation_greedy_oracle.npz'), **out)
+
+
 def make_beamformer(ref):
     bf = ref.beamformer
     F, D, T, K = 9, 6, 80, 3
@@ -242,6 +273,7 @@ def main():
     make_cacg_steps(ref)
     make_cwmm(ref)
     make_permutation(ref)
+    make_permutation_greedy_oracle(ref)
     make_beamformer(ref)
     make_bf_wrapper(ref)
     total = 0

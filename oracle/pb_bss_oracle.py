@@ -435,6 +435,54 @@ def dhtv_calculate_mapping(mask, plan):
     return mapping
 
 
+def score_matrix(mask, reference_mask, similarity_metric):
+    """(K, F, T) x (K, F, T) -> (F, k_ref, K_mask), pb_bss/permutation_alignment.py:380-420."""
+    if similarity_metric == 'cos':
+        mask, reference_mask = _vector_norm(mask), _vector_norm(reference_mask)
+    if similarity_metric in ('cos', 'multiply'):
+        return np.einsum('KFT,kFT->FkK', mask, reference_mask)
+    if similarity_metric == 'euclidean':
+        d = np.sqrt(np.sum(np.abs(mask[None] - reference_mask[:, None]) ** 2, axis=-1))  # (k, K, F)
+        return -np.moveaxis(d, -1, 0)
+    raise ValueError(similarity_metric)
+
+
+def optimal_mapping_from_score_matrix(score):
+    """score (K, K) -> first best of itertools.permutations (pb_bss/permutation_alignment.py:556-585)."""
+    import itertools
+    K = score.shape[-1]
+    best, best_perm = float('-inf'), None
+    for perm in itertools.permutations(range(K)):
+        s = sum(score[range(K), perm])
+        if s > best:
+            best, best_perm = s, perm
+    return np.asarray(best_perm, dtype=np.int64)
+
+
+def mapping_from_score_matrix(scores, algorithm):
+    """scores (F, K, K) -> mapping (K, F), pb_bss/permutation_alignment.py:458-590."""
+    if not np.all(np.isfinite(scores)):
+        raise ValueError('score matrix is infeasible')
+    fn = {'greedy': greedy_mapping_from_score_matrix, 'optimal': optimal_mapping_from_score_matrix}[algorithm]
+    return np.stack([fn(sc) for sc in scores], axis=1)
+
+
+def greedy_permutation_alignment(mask, similarity_metric='euclidean'):
+    """GreedyPermutationAlignment.calculate_mapping, pb_bss/permutation_alignment.py:612-714
+    (the pairwise assignment is always 'greedy', :703)."""
+    K, F, _ = mask.shape
+    pair = mapping_from_score_matrix(score_matrix(mask[:, 1:], mask[:, :-1], similarity_metric), 'greedy')
+    mapping = np.concatenate([np.arange(K)[:, None], pair], axis=1)
+    for f in range(1, F):
+        mapping[:, f] = mapping[mapping[:, f - 1], f]
+    return mapping
+
+
+def oracle_permutation_alignment(mask, reference_mask, similarity_metric='euclidean', algorithm='optimal'):
+    """OraclePermutationAlignment.calculate_mapping, pb_bss/permutation_alignment.py:723-786."""
+    return mapping_from_score_matrix(score_matrix(mask, reference_mask, similarity_metric), algorithm)
+
+
 def apply_mapping(mask, mapping):
     """pb_bss/permutation_alignment.py:54-104."""
     K, F = mapping.shape

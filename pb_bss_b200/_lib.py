@@ -65,6 +65,9 @@ SIGNATURES = {
     'pbb_dhtv_scratch_doubles': (_sz, [_i, _i, ctypes.POINTER(_i), _i]),
     'pbb_dhtv_mapping': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     'pbb_apply_mapping': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    'pbb_score_matrix': (_i, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp]),
+    'pbb_mapping_from_score_matrix': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    'pbb_chain_mapping': (_i, [_vp, _i, _i, _vp, _vp]),
     'pbb_rank_one_estimate': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_matvec_batched': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_apply_beamforming_vector': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -144,6 +144,120 @@ __global__ void apply_mapping_kernel(const double* __restrict__ mask, const long
   for (int t = threadIdx.x; t < T; t += blockDim.x) o[t] = s[t];
 }
 
+// ---- score matrices and assignments for Greedy / Oracle alignment ------------------
+// _ScoreMatrix.multiply / cos / euclidean (:380-420): scores[f][k_ref][k_mask].  One warp
+// per bin; the bin-th vector of source k starts at base + k * source_stride + f * T, which
+// lets GreedyPermutationAlignment pass the two shifted views mask[:, 1:] / mask[:, :-1]
+// (:702) of one array.
+__global__ void __launch_bounds__(128) score_matrix_kernel(const double* __restrict__ mask,
+                                                           const double* __restrict__ ref, long long mask_ss,
+                                                           long long ref_ss, int K, int F, int T, int metric,
+                                                           double* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (f >= F) return;
+  double nm[kDhtvMaxK], nr[kDhtvMaxK];
+  for (int k = 0; k < K; ++k) { nm[k] = 1.0; nr[k] = 1.0; }
+  if (metric == 1) {  // cos: both sides L2-normalised over time (:358-377)
+    for (int k = 0; k < K; ++k) {
+      const double* __restrict__ a = mask + k * mask_ss + (size_t)f * T;
+      const double* __restrict__ b = ref + k * ref_ss + (size_t)f * T;
+      double sa = 0.0, sb = 0.0;
+      for (int t = lane; t < T; t += 32) { sa += a[t] * a[t]; sb += b[t] * b[t]; }
+      nm[k] = fmax(sqrt(warp_sum(sa)), kTiny);
+      nr[k] = fmax(sqrt(warp_sum(sb)), kTiny);
+    }
+  }
+  for (int kr = 0; kr < K; ++kr)
+    for (int km = 0; km < K; ++km) {
+      const double* __restrict__ a = mask + km * mask_ss + (size_t)f * T;
+      const double* __restrict__ b = ref + kr * ref_ss + (size_t)f * T;
+      double s = 0.0;
+      if (metric == 2) {
+        for (int t = lane; t < T; t += 32) { const double d = a[t] - b[t]; s += d * d; }
+        s = -sqrt(warp_sum(s));  // the minus turns the distance into a similarity (:412-418)
+      } else {
+        for (int t = lane; t < T; t += 32) s += (a[t] / nm[km]) * (b[t] / nr[kr]);
+        s = warp_sum(s);
+      }
+      if (lane == 0) scores[((size_t)f * K + kr) * K + km] = s;
+    }
+}
+
+// _mapping_from_score_matrix (:458-590), one thread per bin.  greedy: K times the first
+// maximum of the row-major flattened matrix, then blank its row and column; optimal: the
+// first best of itertools.permutations(range(K)) (lexicographic order, strict >), the score
+// of a permutation summed left to right like Python's sum().
+__global__ void mapping_from_score_kernel(const double* __restrict__ scores, int F, int K, int optimal,
+                                          long long* __restrict__ mapping, int* __restrict__ status) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  double sc[kDhtvMaxK * kDhtvMaxK];
+  bool finite = true;
+  for (int i = 0; i < K * K; ++i) {
+    sc[i] = scores[(size_t)f * K * K + i];
+    finite = finite && isfinite(sc[i]);
+  }
+  if (!finite) {  // ValueError('score matrix is infeasible') (:511-513)
+    atomicCAS(status, 0, f + 1);
+    for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = k;
+    return;
+  }
+  int out[kDhtvMaxK];
+  if (!optimal) {
+    for (int r = 0; r < K; ++r) {
+      int bi = 0, bj = 0;
+      double best = -INFINITY;
+      bool found = false;
+      for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+          const double v = sc[i * K + j];
+          if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
+        }
+      for (int j = 0; j < K; ++j) sc[bi * K + j] = -INFINITY;
+      for (int i = 0; i < K; ++i) sc[i * K + bj] = -INFINITY;
+      out[bi] = bj;
+    }
+  } else {
+    int perm[kDhtvMaxK];
+    for (int k = 0; k < K; ++k) { perm[k] = k; out[k] = k; }
+    double best = -INFINITY;
+    while (true) {
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) s += sc[k * K + perm[k]];
+      if (s > best) {
+        best = s;
+        for (int k = 0; k < K; ++k) out[k] = perm[k];
+      }
+      int i = K - 2;  // next lexicographic permutation
+      while (i >= 0 && perm[i] > perm[i + 1]) --i;
+      if (i < 0) break;
+      int j = K - 1;
+      while (perm[j] < perm[i]) --j;
+      int tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+      for (int a = i + 1, b = K - 1; a < b; ++a, --b) { tmp = perm[a]; perm[a] = perm[b]; perm[b] = tmp; }
+    }
+  }
+  for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = out[k];
+}
+
+// GreedyPermutationAlignment.calculate_mapping (:700-712): bin 0 is the identity, bins
+// 1..F-1 hold the pairwise mappings to their lower neighbour; chain them bottom up,
+// mapping[:, f] = mapping[mapping[:, f-1], f].  Sequential in f by definition; K lanes.
+__global__ void chain_mapping_kernel(const long long* __restrict__ pair, int K, int F, long long* __restrict__ mapping) {
+  const int k = threadIdx.x;
+  __shared__ long long prev[kDhtvMaxK];
+  if (k < K) { prev[k] = k; mapping[(size_t)k * F] = k; }
+  __syncthreads();
+  for (int f = 1; f < F; ++f) {
+    long long v = 0;
+    if (k < K) v = pair[(size_t)prev[k] * (F - 1) + (f - 1)];
+    __syncthreads();
+    if (k < K) { prev[k] = v; mapping[(size_t)k * F + f] = v; }
+    __syncthreads();
+  }
+}
+
 }  // namespace pbb
 
 using namespace pbb;
@@ -210,6 +324,50 @@ int pbb_apply_mapping(const double* mask, const long long* mapping, int K, int F
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LaunchScope ls("apply_mapping_kernel", st);
   apply_mapping_kernel<<<K * F, 128, 0, st>>>(mask, mapping, K, F, T, out);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pbb_score_matrix(const double* mask, const double* reference, long long mask_source_stride,
+                     long long reference_source_stride, int K, int F, int T, int metric, double* scores,
+                     void* stream) {
+  PBB_CHECK_ARG(mask != nullptr, 1, "mask is null");
+  PBB_CHECK_ARG(reference != nullptr, 2, "reference mask is null");
+  PBB_CHECK_ARG(K > 0 && K <= kDhtvMaxK, 5, "need 0 < K < 10 (permutation_alignment.py:690)");
+  PBB_CHECK_ARG(F > 0 && T > 0, 6, "F and T must be positive");
+  PBB_CHECK_ARG(metric >= 0 && metric <= 2, 8, "metric: 0 multiply, 1 cos, 2 euclidean");
+  PBB_CHECK_ARG(scores != nullptr, 9, "scores is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("score_matrix_kernel", st);
+  score_matrix_kernel<<<(F + 3) / 4, 128, 0, st>>>(mask, reference, mask_source_stride, reference_source_stride, K,
+                                                   F, T, metric, scores);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pbb_mapping_from_score_matrix(const double* scores, int F, int K, int algorithm, long long* mapping,
+                                  int* status, void* stream) {
+  PBB_CHECK_ARG(scores != nullptr, 1, "scores is null");
+  PBB_CHECK_ARG(F > 0, 2, "F must be positive");
+  PBB_CHECK_ARG(K > 0 && K <= kDhtvMaxK, 3, "need 0 < K < 10");
+  PBB_CHECK_ARG(algorithm == 0 || algorithm == 1, 4, "algorithm: 0 greedy, 1 optimal");
+  PBB_CHECK_ARG(mapping != nullptr, 5, "mapping is null");
+  PBB_CHECK_ARG(status != nullptr, 6, "status is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("mapping_from_score_kernel", st);
+  mapping_from_score_kernel<<<(F + 63) / 64, 64, 0, st>>>(scores, F, K, algorithm, mapping, status);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int pbb_chain_mapping(const long long* pair_mapping, int K, int F, long long* mapping, void* stream) {
+  PBB_CHECK_ARG(pair_mapping != nullptr || F == 1, 1, "pair mapping is null");
+  PBB_CHECK_ARG(K > 0 && K <= kDhtvMaxK, 2, "need 0 < K < 10");
+  PBB_CHECK_ARG(F > 0, 3, "F must be positive");
+  PBB_CHECK_ARG(mapping != nullptr, 4, "mapping is null");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LaunchScope ls("chain_mapping_kernel", st);
+  chain_mapping_kernel<<<1, 32, 0, st>>>(pair_mapping, K, F, mapping);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,7 +1,9 @@
 """Frequency permutation alignment on the device, API of pb_bss/permutation_alignment.py.
 
-``DHTVPermutationAlignment`` (segment-wise centroid matching, :133-355) and
-``apply_mapping`` (:54-104) run in CUDA (``pbb_dhtv_mapping`` /
+``DHTVPermutationAlignment`` (segment-wise centroid matching, :133-355),
+``GreedyPermutationAlignment`` (:592-714), ``OraclePermutationAlignment``
+(:717-786) and ``apply_mapping`` (:54-104) run in CUDA (``pbb_dhtv_mapping``,
+``pbb_score_matrix``, ``pbb_mapping_from_score_matrix``, ``pbb_chain_mapping``,
 ``pbb_apply_mapping``); the alignment plan is host logic.
 """
 import ctypes
@@ -11,7 +13,8 @@ import torch
 
 from . import _device, _lib
 
-__all__ = ['DHTVPermutationAlignment', 'apply_mapping', 'interleave',
+__all__ = ['DHTVPermutationAlignment', 'GreedyPermutationAlignment',
+           'OraclePermutationAlignment', 'apply_mapping', 'interleave',
            'sample_random_mapping']
 
 
@@ -143,3 +146,116 @@ class DHTVPermutationAlignment(_PermutationAlignment):
                                         _device.ptr(feat), _device.ptr(cent), _device.ptr(mapping),
                                         _device.stream_ptr()), 'pbb_dhtv_mapping')
         return _device.to_host(mapping, like_numpy)
+
+
+_METRICS = {'multiply': 0, 'cos': 1, 'euclidean': 2}
+_ALGORITHMS = {'greedy': 0, 'optimal': 1}
+
+
+def _metric_code(similarity_metric):
+    """_ScoreMatrix.from_name (:420-441): unknown names raise with the suggestions."""
+    try:
+        return _METRICS[similarity_metric]
+    except (KeyError, TypeError):
+        raise AttributeError(
+            f"type object '_ScoreMatrix' has no attribute {similarity_metric!r}\n"
+            'Suggestions: cos, euclidean, from_name, multiply') from None
+
+
+def _score_matrix(mask, reference_mask, metric, F, source_strides=None):
+    """(K, F, T) device masks -> scores (F, K, K) on the device (:380-420).
+
+    ``source_strides`` = element strides between sources of (mask, reference)
+    when they are views with F bins into larger arrays.
+    """
+    K, _, T = mask.shape
+    ms, rs = source_strides or (mask.shape[1] * T, reference_mask.shape[1] * T)
+    scores = _device.empty((F, K, K), torch.float64)
+    lib = _lib.load()
+    _lib.check(lib.pbb_score_matrix(_device.ptr(mask), _device.ptr(reference_mask), ms, rs, K, F, T, metric,
+                                    _device.ptr(scores), _device.stream_ptr()), 'pbb_score_matrix')
+    return scores
+
+
+def _mapping_from_score_matrix(score_matrix, algorithm='optimal'):
+    """score_matrix (..., K, K) -> mapping (K, ...) (:458-590)."""
+    like_numpy = not _device.is_tensor(score_matrix)
+    sc = _device.to_device(np.asanyarray(score_matrix) if like_numpy else score_matrix).to(torch.float64)
+    *F, K, K_ = sc.shape
+    assert K == K_, (tuple(sc.shape), K, K_)
+    if algorithm not in _ALGORITHMS:
+        raise ValueError(algorithm)
+    n = int(np.prod(F)) if F else 1
+    sc = sc.reshape(n, K, K).contiguous()
+    mapping = _device.empty((K, n), torch.int64)
+    status = torch.zeros(1, dtype=torch.int32, device=sc.device)
+    lib = _lib.load()
+    _lib.check(lib.pbb_mapping_from_score_matrix(_device.ptr(sc), n, K, _ALGORITHMS[algorithm],
+                                                 _device.ptr(mapping), _device.ptr(status),
+                                                 _device.stream_ptr()), 'pbb_mapping_from_score_matrix')
+    if int(status.item()):
+        # message of scipy.optimize.linear_sum_assignment, like the reference (:511-513)
+        raise ValueError('score matrix is infeasible')
+    return _device.to_host(mapping.reshape(K, *F), like_numpy)
+
+
+class GreedyPermutationAlignment(_PermutationAlignment):
+    """Align every bin to its lower neighbour, then chain the mappings (:592-714).
+
+    As in the reference the pairwise assignment is always the greedy one; the
+    ``algorithm`` argument is stored but not used (:702-703).
+    """
+
+    def __init__(self, similarity_metric='euclidean', algorithm='optimal'):
+        try:
+            self._metric = _metric_code(similarity_metric)
+        except Exception:
+            raise ValueError(similarity_metric)
+        self.similarity_metric = similarity_metric
+        self.algorithm = algorithm
+
+    def calculate_mapping(self, mask):
+        """mask (K, F, T) -> mapping (K, F) int64 (:612-714)."""
+        like_numpy = not _device.is_tensor(mask)
+        m = _device.to_device(mask).to(torch.float64).contiguous()
+        K, F, T = m.shape
+        assert K < 10, (K, 'Sure?')
+        assert F % 2 == 1, (F, 'Sure? Usually F is odd.', tuple(m.shape))
+        lib = _lib.load()
+        mapping = _device.empty((K, F), torch.int64)
+        pair = None
+        if F > 1:
+            # scores between mask[:, 1:] and mask[:, :-1]: two views of the same array
+            scores = _device.empty((F - 1, K, K), torch.float64)
+            _lib.check(lib.pbb_score_matrix(_device.ptr(m) + T * 8, _device.ptr(m), F * T, F * T, K, F - 1, T,
+                                            self._metric, _device.ptr(scores), _device.stream_ptr()),
+                       'pbb_score_matrix')
+            pair = _mapping_from_score_matrix(scores, 'greedy')
+        _lib.check(lib.pbb_chain_mapping(_device.ptr(pair), K, F, _device.ptr(mapping), _device.stream_ptr()),
+                   'pbb_chain_mapping')
+        return _device.to_host(mapping, like_numpy)
+
+
+class OraclePermutationAlignment(_PermutationAlignment):
+    """Align every bin to a reference mask (:717-786)."""
+
+    def __init__(self, similarity_metric='euclidean', algorithm='optimal'):
+        assert algorithm in ['greedy', 'optimal'], algorithm
+        self._metric = _metric_code(similarity_metric)
+        self.similarity_metric = similarity_metric
+        self.algorithm = algorithm
+
+    def calculate_mapping(self, mask, reference_mask):
+        """mask, reference_mask (K, F, T) -> mapping (K, F) int64 (:723-786)."""
+        like_numpy = not _device.is_tensor(mask)
+        m = _device.to_device(mask).to(torch.float64).contiguous()
+        r = _device.to_device(reference_mask).to(torch.float64).contiguous()
+        assert m.shape == r.shape, (tuple(m.shape), tuple(r.shape))
+        K, *F, T = m.shape
+        assert K < 10, (K, 'Sure?')
+        if len(F) == 1:
+            assert F[0] % 2 == 1, (F, 'Sure? Usually F is odd.', tuple(m.shape))
+        n = int(np.prod(F)) if F else 1
+        scores = _score_matrix(m.reshape(K, n, T), r.reshape(K, n, T), self._metric, n)
+        mapping = _mapping_from_score_matrix(scores, self.algorithm)
+        return _device.to_host(mapping.reshape(K, *F), like_numpy)

@@ -188,3 +188,30 @@ def test_beamformer_chain():
     obs = np.array([[0, 0, 1], [0, 0.1, 1], [0.1, 0, 1]])
     w, _ = O.mvdr_vector_souden((obs.T.conj() @ obs)[None], np.eye(3)[None])
     np.testing.assert_allclose(w[0], [0.03311258, 0.03311258, 0.99337748], atol=1e-8)
+
+
+METRICS = ('cos', 'euclidean', 'multiply')
+
+
+@pytest.mark.parametrize('metric', METRICS)
+def test_greedy_and_oracle_permutation_alignment(metric):
+    # GreedyPermutationAlignment / OraclePermutationAlignment, permutation_alignment.py:592-786
+    g = load_golden('permutation_greedy_oracle')
+    np.testing.assert_allclose(O.score_matrix(g['noise'], g['noise_reference'], metric), g[f'scores_{metric}'],
+                               rtol=1e-13, atol=1e-15)
+    for tag, mask, ref in (('', g['mask'], g['reference_mask']), ('noise_', g['noise'], g['noise_reference'])):
+        np.testing.assert_array_equal(O.greedy_permutation_alignment(mask, metric), g[f'greedy_{tag}{metric}'])
+        for alg in ('greedy', 'optimal'):
+            np.testing.assert_array_equal(O.oracle_permutation_alignment(mask, ref, metric, alg),
+                                          g[f'oracle_{tag}{metric}_{alg}'])
+
+
+def test_mapping_from_score_matrix_doctest():
+    # permutation_alignment.py:475-508: 'optimal' and 'greedy' differ on this matrix
+    g = load_golden('permutation_greedy_oracle')
+    np.testing.assert_array_equal(O.greedy_mapping_from_score_matrix(g['score']), [0, 2, 1])
+    np.testing.assert_array_equal(O.optimal_mapping_from_score_matrix(g['score']), [1, 2, 0])
+    np.testing.assert_array_equal(g['score_greedy'], [0, 2, 1])
+    np.testing.assert_array_equal(g['score_optimal'], [1, 2, 0])
+    with pytest.raises(ValueError, match='infeasible'):
+        O.mapping_from_score_matrix(np.array([[[np.inf, 0], [1, 2]]]), 'optimal')

@@ -62,3 +62,60 @@ def test_apply_mapping_trailing_dims_and_device_tensors():
     out = apply_mapping(torch.from_numpy(mask).cuda(), torch.from_numpy(mapping).cuda())
     assert out.is_cuda
     np.testing.assert_array_equal(out.cpu().numpy(), mask[mapping, range(F)])
+
+
+METRICS = ('cos', 'euclidean', 'multiply')
+
+
+@pytest.mark.parametrize('metric', METRICS)
+def test_greedy_and_oracle_alignment_match_reference_golden(metric):
+    """GreedyPermutationAlignment / OraclePermutationAlignment (permutation_alignment.py:592-786):
+    exact integer equality with the mappings of the unmodified reference."""
+    from pb_bss_b200.permutation_alignment import GreedyPermutationAlignment, OraclePermutationAlignment
+    g = load_golden('permutation_greedy_oracle')
+    for tag, mask, ref in (('', g['mask'], g['reference_mask']), ('noise_', g['noise'], g['noise_reference'])):
+        got = GreedyPermutationAlignment(metric).calculate_mapping(mask)
+        assert got.dtype == np.int64
+        np.testing.assert_array_equal(got, g[f'greedy_{tag}{metric}'])
+        for alg in ('greedy', 'optimal'):
+            al = OraclePermutationAlignment(metric, alg)
+            np.testing.assert_array_equal(al.calculate_mapping(mask, ref), g[f'oracle_{tag}{metric}_{alg}'])
+    # the oracle alignment undoes the random permutation of the synthetic mask
+    aligned = OraclePermutationAlignment(metric)(g['mask'], g['reference_mask'])
+    np.testing.assert_array_equal(aligned, g['reference_mask'])
+
+
+def test_mapping_from_score_matrix_known_answers_and_errors():
+    from pb_bss_b200.permutation_alignment import (GreedyPermutationAlignment, OraclePermutationAlignment,
+                                                   _mapping_from_score_matrix)
+    sm = np.array([[11, 10, 0], [4, 5, 10], [6, 0, 5]])  # doctest, permutation_alignment.py:475-508
+    np.testing.assert_array_equal(_mapping_from_score_matrix(sm, 'optimal'), [1, 2, 0])
+    np.testing.assert_array_equal(_mapping_from_score_matrix(sm, 'greedy'), [0, 2, 1])
+    np.testing.assert_array_equal(_mapping_from_score_matrix([sm, sm], 'optimal'), [[1, 1], [2, 2], [0, 0]])
+    with pytest.raises(ValueError, match='infeasible'):
+        _mapping_from_score_matrix([[np.inf, 0], [1, 2]])
+    with pytest.raises(ValueError):
+        _mapping_from_score_matrix(sm, 'hungarian')
+    with pytest.raises(ValueError):
+        GreedyPermutationAlignment('coss')
+    with pytest.raises(AttributeError, match='Suggestions'):
+        OraclePermutationAlignment('coss')
+    with pytest.raises(AssertionError):
+        GreedyPermutationAlignment('cos').calculate_mapping(np.ones((3, 4, 5)))  # even F
+
+
+def test_full_size_greedy_alignment_against_the_oracle():
+    """F=513, K=3, T=500 (C3 shapes): the device mapping equals the NumPy restatement."""
+    from pb_bss_b200.permutation_alignment import GreedyPermutationAlignment
+    rng = np.random.RandomState(5)
+    K, F, T = 3, 513, 500
+    proto = rng.uniform(size=(K, 1, T)) ** 4
+    mask = proto + 0.5 * rng.uniform(size=(K, F, T))
+    mask /= mask.sum(0, keepdims=True)
+    perm = np.stack([rng.permutation(K) for _ in range(F)], axis=1)
+    mask = mask[perm, np.arange(F)]
+    got = GreedyPermutationAlignment('cos').calculate_mapping(mask)
+    np.testing.assert_array_equal(got, O.greedy_permutation_alignment(mask, 'cos'))
+    aligned = mask[got, np.arange(F)]
+    # every bin now carries the same source order as bin 0
+    assert (np.argmax(np.einsum('kft,jt->fkj', aligned, aligned[:, 0]), axis=-1) == np.arange(K)).all()
