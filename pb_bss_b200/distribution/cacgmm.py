@@ -153,6 +153,8 @@ class CACGMMTrainer:
             inline_permutation_aligner=None,
             frames_per_block=0,
             multi_kernel=False,
+            total_bins=None,
+            bin_group=None,
     ):
         """EM for the cACGMM, signature of cacgmm.py:142-157.
 
@@ -168,6 +170,10 @@ class CACGMMTrainer:
             frames_per_block: tuning knob of the multi-kernel EM path (0 = default).
             multi_kernel: force the one-kernel-pair-per-iteration path instead
                 of the persistent kernel (A/B testing; same results).
+            total_bins, bin_group: bin-sharded multi-GPU use (pb_bss_b200.parallel):
+                ``y`` holds this rank's contiguous slice of ``total_bins`` bins.  Only
+                the couplings across bins (frequency-tied weights, inline alignment)
+                communicate, once per iteration.
         Returns: CACGMM
         """
         assert xor(initialization is None, num_classes is None), (
@@ -213,7 +219,7 @@ class CACGMMTrainer:
             return self._fit_coupled(
                 yd, like_numpy, init_dev, model_in, K, iterations, saliency, source_activity_mask,
                 weight_mode, hermitize, covariance_norm, affiliation_eps, eigenvalue_floor,
-                inline_permutation_aligner, weight_constant_axis)
+                inline_permutation_aligner, weight_constant_axis, total_bins, bin_group)
 
         act = None
         if source_activity_mask is not None:
@@ -271,13 +277,17 @@ class CACGMMTrainer:
 
     def _fit_coupled(self, yd, like_numpy, init_dev, model_in, K, iterations, saliency, source_activity_mask,
                      weight_mode, hermitize, covariance_norm, affiliation_eps, eigenvalue_floor, aligner,
-                     weight_constant_axis):
+                     weight_constant_axis, total_bins=None, bin_group=None):
         """EM with per-iteration coupling across bins: frequency-tied mixture weights
         (``weight_constant_axis`` (-3,) / (-3, -1), mixture_model_utils.py:187-190) and / or the
         inline permutation alignment (mixture_model_utils.py:264-306).  Every step runs on the
         device; the loop itself is the reference's (cacgmm.py:252-278)."""
+        from .. import parallel
         from ..permutation_alignment import apply_mapping
         independent, F, N, D = _flatten_obs(yd)
+        F_all = F if total_bins is None else int(total_bins)
+        lo, hi = parallel.local_bins(F_all, bin_group) if F_all != F else (0, F)
+        assert hi - lo == F, ('this rank holds bins', (lo, hi), 'but y has', F)
         tied = weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED)
         if aligner is not None:
             message = ('Inline permutation alignment reduces mismatch between frequency independent '
@@ -298,7 +308,11 @@ class CACGMMTrainer:
                     yd, source_activity_mask, affiliation_eps, want_q=True)
                 if aligner is not None:
                     mask_kft = affiliation.permute(1, 0, 2).contiguous()
-                    mapping = aligner.calculate_mapping(mask_kft)
+                    if F_all != F:  # the alignment needs every bin: gather, align replicated, keep the slice
+                        every = parallel.all_gather_bins(affiliation.contiguous(), F_all, bin_group)
+                        mapping = aligner.calculate_mapping(every.permute(1, 0, 2).contiguous())[:, lo:hi].contiguous()
+                    else:
+                        mapping = aligner.calculate_mapping(mask_kft)
                     affiliation = apply_mapping(mask_kft, mapping).permute(1, 0, 2).contiguous()
                     quadratic_form = apply_mapping(quadratic_form.permute(1, 0, 2).contiguous(),
                                                    mapping).permute(1, 0, 2).contiguous()
@@ -313,6 +327,9 @@ class CACGMMTrainer:
                 _lib.check(lib.pbb_mixture_weight_over_bins(
                     _device.ptr(aff), F, K, N, int(weight_mode == _lib.WEIGHT_TIED), _device.ptr(w_kt),
                     _device.ptr(w_k), _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
+                if F_all != F:  # sum over the other ranks' bins
+                    w_kt = parallel.mean_over_all_bins(w_kt, F, F_all, bin_group)
+                    w_k = parallel.mean_over_all_bins(w_k, F, F_all, bin_group)
                 model.weight = w_kt[None] if weight_mode == _lib.WEIGHT_TIED_TIME else w_k[None, :, None]
         if like_numpy:
             model = CACGMM(

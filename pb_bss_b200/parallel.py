@@ -6,6 +6,10 @@ NO data-path collective.  The only exchange is one all-gather of the per-bin
 affiliations (F, K, T) before the frequency permutation alignment, whose
 centroids couple the bins of a segment (permutation_alignment.py:334); the
 alignment then runs replicated and each rank keeps its slice of the result.
+The non-default couplings inside the EM loop add one small collective per
+iteration: an all-reduce of the (K, T) / (K,) weight sums for frequency-tied
+weights and the same all-gather for the inline permutation alignment
+(``CACGMMTrainer.fit(..., total_bins=F, bin_group=group)``).
 
 ``torch.distributed`` is only the transport (NCCL over NVLink on the GPUs; the
 same code runs over gloo on CPU tensors, which is how the host logic is
@@ -17,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['world', 'bin_shards', 'local_bins', 'all_gather_bins',
-           'sharded_separation']
+           'mean_over_all_bins', 'sharded_separation']
 
 
 def world(group=None):
@@ -64,6 +68,21 @@ def all_gather_bins(local, F, group=None):
     dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
     out = out.reshape(ws, nmax, *local.shape[1:])
     return torch.cat([out[r, :h - l] for r, (l, h) in enumerate(shards)], dim=0)
+
+
+def mean_over_all_bins(local_mean, n_local, F, group=None):
+    """Mean over ALL F bins from every rank's mean over its n_local bins.
+
+    The per-iteration exchange of frequency-tied mixture weights
+    (``weight_constant_axis`` (-3,) / (-3, -1), mixture_model_utils.py:187-190):
+    one all-reduce of (K, T) or (K,) doubles, latency bound over NVLink."""
+    rank, ws = world(group)
+    if ws == 1:
+        assert n_local == F, (n_local, F)
+        return local_mean
+    total = local_mean * float(n_local)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total / float(F)
 
 
 def sharded_separation(y_local, initialization_local, F, *, iterations=100,

@@ -45,6 +45,11 @@ def _worker(rank, ws, port, F, q):
         # integer payloads (mappings) travel the same way
         m = torch.arange(F * 2, dtype=torch.int64).reshape(F, 2)
         ok = ok and bool(torch.equal(all_gather_bins(m[lo:hi].clone(), F), m))
+        # frequency-tied weights: global mean over bins from the ranks' local means
+        from pb_bss_b200.parallel import mean_over_all_bins
+        aff = torch.rand(F, 3, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+        got = mean_over_all_bins(aff[lo:hi].mean(0), hi - lo, F)
+        ok = ok and bool(torch.allclose(got, aff.mean(0), rtol=1e-13, atol=0))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -71,3 +76,6 @@ def test_single_rank_degrades_gracefully():
     assert local_bins(513) == (0, 513)
     x = torch.randn(7, 2, 3)
     assert all_gather_bins(x, 7) is x
+    from pb_bss_b200.parallel import mean_over_all_bins
+    x0 = x[0]
+    assert mean_over_all_bins(x0, 7, 7) is x0
