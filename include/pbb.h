@@ -61,6 +61,7 @@ void pbb_profile_reset(void);
  * total device time (ms) and its launch count, and clears the records.
  * Synchronises on the recorded events.  Return value: number of distinct kernels. */
 int pbb_profile_dominant(char* name, int name_len, double* total_ms, int* launches);
+void pbb_profile_dump(void); /* every recorded launch to stderr */
 
 /* ------------------------------------------------------------------------
  * Observation normalisation.
@@ -90,7 +91,8 @@ typedef struct pbb_cacgmm_options {
   double affiliation_eps;  /* clip of the posterior, cacgmm.py:154 */
   double eigenvalue_floor; /* cacgmm.py:155 */
   int frames_per_block;    /* 0 = library default; tuning knob */
-  int reserved;            /* bit 0: force the multi-kernel (non-persistent) path */
+  int reserved;            /* bit 0: force the multi-kernel (non-persistent) path;
+                              bit 1: no streamed upload (see pbb_cacgmm_fit) */
 } pbb_cacgmm_options;
 
 /* Bytes of scratch pbb_cacgmm_fit / _predict need for this problem size. */
@@ -105,6 +107,13 @@ size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K);
  *  activity     (F, K, T) uint8 source_activity_mask or NULL
  *  outputs      eigenvectors, eigenvalues, weight as described above
  *  status       device int, see header comment
+ * Host buffers: y, init_aff and the three outputs may also be PINNED
+ * (page-locked, mapped) host memory; the kernels then read / write them in place
+ * over PCIe.  With y pinned and init_aff given, a small loader kernel on an
+ * internal side stream streams the bins in while the EM kernel already iterates
+ * on the bins that have arrived (task order: see em_persistent.cuh; the order
+ * table, 4 bytes per task, lives in a small library-owned device cache).  The
+ * call stays asynchronous with respect to `stream`.
  */
 int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K,
                    const double* init_aff, const double* saliency,

@@ -25,9 +25,17 @@ def is_tensor(x):
     return isinstance(x, torch.Tensor)
 
 
-def to_device(x, dtype=None):
-    """numpy array / torch tensor -> contiguous CUDA tensor (copy only if needed)."""
+def to_device(x, dtype=None, keep_pinned=False):
+    """numpy array / torch tensor -> contiguous CUDA tensor (copy only if needed).
+
+    ``keep_pinned``: a contiguous CPU tensor in pinned (page-locked) memory is returned as
+    it is -- the library reads such buffers in place over PCIe (include/pbb.h,
+    pbb_cacgmm_fit), which overlaps the upload with the computation.
+    """
     dev = device()
+    if (keep_pinned and is_tensor(x) and x.device.type == 'cpu' and x.is_pinned() and x.is_contiguous()
+            and (dtype is None or x.dtype == dtype)):
+        return x
     if not is_tensor(x):
         x = np.asarray(x)
         if not x.flags.c_contiguous:

@@ -38,6 +38,7 @@ SIGNATURES = {
     'pbb_launch_count': (ctypes.c_longlong, []),
     'pbb_profile_enable': (None, [_i]),
     'pbb_profile_reset': (None, []),
+    'pbb_profile_dump': (None, []),
     'pbb_profile_dominant': (_i, [ctypes.c_char_p, _i, ctypes.POINTER(_d), ctypes.POINTER(_i)]),
     'pbb_normalize_observation': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'pbb_cacgmm_workspace_bytes': (_sz, [_i, _i, _i, _i]),

@@ -1,6 +1,12 @@
 // C-ABI entry points for the cACGMM EM path (see include/pbb.h).
+#include <algorithm>
+#include <array>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
@@ -75,10 +81,12 @@ struct CacgmmWorkspace {
   double* w;
   double* ew;
   double* loglik_part;
+  double* aff_stage;  // (F, K, T) device copy of host-resident initial affiliations (streamed upload)
   size_t bytes;
 };
 
 static int max_chunks(int T) { return (T + 31) / 32; }
+constexpr int kMaxOrder = 1 << 20;  // tasks (bins x iterations) an explicit task order may have
 
 static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   CacgmmWorkspace ws;
@@ -98,6 +106,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t o_w = take((size_t)F * K * sizeof(double));
   const size_t o_ew = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
   const size_t o_ll = take((size_t)F * max_chunks(T) * sizeof(double));
+  const size_t o_aff = take((size_t)F * K * T * sizeof(double));
   char* b = reinterpret_cast<char*>(base);
   ws.z = b + o_z;
   ws.zs = zs;
@@ -111,6 +120,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   ws.w = reinterpret_cast<double*>(b + o_w);
   ws.ew = reinterpret_cast<double*>(b + o_ew);
   ws.loglik_part = reinterpret_cast<double*>(b + o_ll);
+  ws.aff_stage = reinterpret_cast<double*>(b + o_aff);
   ws.bytes = off;
   return ws;
 }
@@ -233,9 +243,121 @@ static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
 }
 
 // ---- persistent kernel launch ---------------------------------------------------
+constexpr int kLoadReserve = 4;  // EM CTA slots left free in streamed-upload mode
+constexpr int kLoadCtas = 16;    // stream_load_kernel grid: <= 4 of its CTAs fit into one free EM slot
+
+// Task order of the streamed upload (em_persistent.cuh).  The bins arrive over PCIe in ascending
+// order, `arrive` per time slot; a slot is one task duration and the machine runs `cap` tasks per
+// slot.  List scheduling: every slot takes the (at most cap) arrived, unfinished bins that have
+// done the FEWEST iterations -- early bins run ahead while the link is the bottleneck, late bins
+// catch up afterwards and all bins finish together instead of leaving a thin tail of late bins.
+// A task still only depends on a lower ticket ((b, it - 1) sits in an earlier slot).
+// The table (4 bytes per task) is built once per (device, F, iterations, arrive, cap) and kept in a
+// small library-owned device cache -- the only device memory the library allocates itself.
+static int streamed_order(int F, int I, int arrive, int cap, const int** out) {
+  static std::mutex mu;
+  static std::map<std::array<int, 5>, int*> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  const std::array<int, 5> key{dev, F, I, arrive, cap};
+  auto hit = cache.find(key);
+  if (hit != cache.end()) { *out = hit->second; return 0; }
+  if (cache.size() >= 16) {
+    for (auto& kv : cache) cudaFree(kv.second);
+    cache.clear();
+  }
+  std::vector<int> order;
+  order.reserve((size_t)F * I);
+  std::vector<int> done(F, 0), count(I + 1), pick;
+  for (long long slot = 0; order.size() < (size_t)F * I; ++slot) {
+    const int arrived = (int)std::min<long long>(F, (long long)arrive * (slot + 1));
+    // threshold = the done-count below which everything is taken, plus a partial level
+    std::fill(count.begin(), count.end(), 0);
+    for (int b = 0; b < arrived; ++b)
+      if (done[b] < I) ++count[done[b]];
+    int level = 0, left = cap;
+    while (level < I && count[level] <= left) left -= count[level++];
+    // all unfinished bins with done < level, and `left` bins of done == level (highest bins first)
+    pick.clear();
+    for (int b = arrived - 1; b >= 0; --b) {
+      if (done[b] >= I) continue;
+      if (done[b] < level) pick.push_back(b);
+      else if (done[b] == level && left > 0) { pick.push_back(b); --left; }
+    }
+    for (auto p = pick.rbegin(); p != pick.rend(); ++p) {
+      order.push_back(*p | (done[*p] << 16));
+      ++done[*p];
+    }
+  }
+  int* d = nullptr;
+  PBB_CUDA(cudaMalloc(&d, order.size() * sizeof(int)));
+  PBB_CUDA(cudaMemcpy(d, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+  cache[key] = d;
+  *out = d;
+  return 0;
+}
+
+// device-usable address of a pinned host allocation, nullptr for device memory, error otherwise
+static int classify_pointer(const void* p, const void** dev_alias, bool* is_host, const char* what) {
+  cudaPointerAttributes at;
+  PBB_CUDA(cudaPointerGetAttributes(&at, p));
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+    *is_host = false;
+    *dev_alias = p;
+    return 0;
+  }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+    *is_host = true;
+    *dev_alias = at.devicePointer;
+    return 0;
+  }
+  set_error("%s must be device memory or pinned (page-locked, mapped) host memory", what);
+  return -1;
+}
+
+// side stream + events for the upload that overlaps the EM kernel (one set per process)
+struct LoadStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static int get_load_stream(LoadStream** out) {
+  static LoadStream ls[16];
+  int dev = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) { set_error("device index %d out of range", dev); return 1; }
+  LoadStream& l = ls[dev];
+  if (l.stream == nullptr) {
+    PBB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    PBB_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    PBB_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    l.device = dev;
+  }
+  *out = &l;
+  return 0;
+}
+
+template <typename CT>
+static int launch_stream_load(const void* y, void* z, const double* aff_src, double* aff_dst, int F, int T, int D, int K,
+                              int* dead, int* flags, int* next_bin, cudaStream_t st) {
+  const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
+  const size_t smem = (size_t)kStageFrames * (D + 1) * sizeof(double2);
+  LaunchScope ls("stream_load_kernel", st);
+  int ctas = kLoadCtas;
+  if (const char* e = getenv("PBB_LOAD_CTAS")) ctas = atoi(e) > 0 ? atoi(e) : ctas;  // tuning override
+  stream_load_kernel<CT><<<ctas < F ? ctas : F, kLoadThreads, smem, st>>>(
+      reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), aff_src, aff_dst, F, T, D, K, stage_rows(D),
+      kStageFrames, nchunks, dead, flags, next_bin);
+  PBB_CUDA(cudaGetLastError());
+  return 0;
+}
 template <typename Kern>
 static int launch_persistent_generic(Kern kern, int threads, size_t smem, int* cache, const PersistArgs& a,
                                      const char* name, cudaStream_t st) {
+  // streamed upload: leave kLoadReserve CTA slots free so that stream_load_kernel's CTAs are
+  // resident whatever order the two launches start in (the EM kernel waits on their flags)
+  const int reserve = a.wait_load ? kLoadReserve : 0;
   if (*cache == 0) {
     PBB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n = 0;
@@ -246,7 +368,8 @@ static int launch_persistent_generic(Kern kern, int threads, size_t smem, int* c
   int dev = 0, sms = 0;
   PBB_CUDA(cudaGetDevice(&dev));
   PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  long long grid = (long long)(*cache) * sms;
+  long long grid = (long long)(*cache) * sms - reserve;
+  if (grid < 1) grid = 1;
   const long long tasks = (long long)a.iterations * a.F;
   if (grid > tasks) grid = tasks;
   LaunchScope ls(name, st);
@@ -384,7 +507,46 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   const bool persistent = fast_shape(D, K) && !(opt->reserved & 1);
   int r;
-  if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
+  // y (and the initial affiliations) may be pinned host memory: the kernels then read them in
+  // place over PCIe.  On the persistent path with an affiliation initialisation that read is a
+  // separate small kernel on a side stream that overlaps the EM kernel ("streamed upload").
+  bool y_host = false, aff_host = false;
+  if ((r = classify_pointer(y, &y, &y_host, "y"))) return r;
+  if (init_aff != nullptr) {
+    const void* alias = nullptr;
+    if ((r = classify_pointer(init_aff, &alias, &aff_host, "initial affiliations"))) return r;
+    init_aff = static_cast<const double*>(alias);
+  }
+  // the model may be written straight into pinned host memory as well (write-only on this path)
+  {
+    bool h = false;
+    const void* alias = nullptr;
+    if ((r = classify_pointer(eigenvectors, &alias, &h, "eigenvectors"))) return r;
+    eigenvectors = const_cast<void*>(alias);
+    if ((r = classify_pointer(eigenvalues, &alias, &h, "eigenvalues"))) return r;
+    eigenvalues = static_cast<double*>(const_cast<void*>(alias));
+    if ((r = classify_pointer(weight, &alias, &h, "weight"))) return r;
+    weight = static_cast<double*>(const_cast<void*>(alias));
+  }
+  const bool streamed = persistent && y_host && init_aff != nullptr && !(opt->reserved & 2) &&
+                        ws.aff_stage != nullptr;
+  if (streamed) {
+    // flags[bin] = -1 until the bin has arrived
+    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
+    PBB_CUDA(cudaMemsetAsync(ws.flags, 0xFF, (size_t)F * sizeof(int), st));
+    PBB_CUDA(cudaMemsetAsync(ws.dead, 0, (size_t)F * sizeof(int), st));
+    LoadStream* l = nullptr;
+    if ((r = get_load_stream(&l))) return r;
+    PBB_CUDA(cudaEventRecord(l->fork, st));
+    PBB_CUDA(cudaStreamWaitEvent(l->stream, l->fork, 0));
+    double* aff_dst = aff_host ? ws.aff_stage : nullptr;
+    r = dtype == PBB_C128
+            ? launch_stream_load<double2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, reinterpret_cast<int*>(ws.phase + 15), l->stream)
+            : launch_stream_load<float2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, reinterpret_cast<int*>(ws.phase + 15), l->stream);
+    if (r) return r;
+    PBB_CUDA(cudaEventRecord(l->join, l->stream));
+    if (aff_host) init_aff = ws.aff_stage;
+  } else if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
     r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)
                           : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, st);
   else
@@ -415,7 +577,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   const bool fast_sm = softmax_fast_ok(D, opt);
   if (persistent) {
     // ---- persistent path: every EM iteration in one launch (em_persistent.cuh) ----
-    PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
+    if (!streamed)
+      PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
     if (init_aff == nullptr) {
       FromEigArgs fe;
       fe.F = F; fe.D = D; fe.K = K;
@@ -437,10 +600,35 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
     p.phase = ws.phase; p.dead = ws.dead;
+    if (streamed) {
+      // bins joining per round ~ round duration / arrival time of one bin (em_persistent.cuh,
+      // decode_ticket): ~12 us rounds at D = 8, K = 3, T = 500 against ~50 GB/s of PCIe reads
+      const double bin_bytes = (double)T * D * (dtype == PBB_C128 ? 16.0 : 8.0) + (aff_host ? 8.0 * K * T : 0.0);
+      const double round_us = 12.0 * (T / 500.0) * (D * D / 64.0) * (K / 3.0);
+      int c = (int)(round_us / (bin_bytes / 50e3) + 0.5);
+      if (const char* e = getenv("PBB_WAVE_C")) c = atoi(e);  // tuning override
+      c = c < 1 ? 1 : (c > F ? F : c);
+      p.wave_c = c;
+      p.wait_load = 1;
+      const long long tasks = (long long)F * opt->iterations;
+      if (tasks <= kMaxOrder && F <= 4096 && opt->iterations < 32768 && !getenv("PBB_NO_ORDER")) {
+        int dev = 0, sms = 0;
+        PBB_CUDA(cudaGetDevice(&dev));
+        PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int cap = 2 * sms - kLoadReserve;
+        if (const char* e = getenv("PBB_ORDER_CAP")) cap = atoi(e);  // tuning override
+        if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
+      }
+    }
     // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
     const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
     const bool full = saliency != nullptr || activity != nullptr || !lean_ok || p.user_model;
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
+    if (streamed) {
+      LoadStream* l = nullptr;
+      if ((r = get_load_stream(&l))) return r;
+      PBB_CUDA(cudaStreamWaitEvent(st, l->join, 0));
+    }
 #ifdef PBB_PHASE_TIMING
     {
       unsigned long long ph[8];

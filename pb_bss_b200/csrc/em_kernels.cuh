@@ -940,4 +940,147 @@ __global__ void normalize_staged_kernel(const CT* __restrict__ y, CT* __restrict
   }
 }
 
+// Streamed upload for the persistent fit: the observation (and the initial affiliations) live
+// in PINNED HOST memory and are read here directly over PCIe while the EM kernel already runs
+// on the bins that have arrived.  A few CTAs take bins from a counter (ascending order; any
+// resident subset of the CTAs makes progress); per bin: normalise + stage the observation exactly
+// like normalize_staged_kernel, copy the bin's initial affiliations to the device, then publish
+// flags[bin] = 0 (release), which is what the bin's first EM task waits for (em_persistent.cuh).
+// The link latency (~2 us) is covered by software pipelining: the 16-byte loads of the NEXT
+// 128-frame chunk (of this bin or the next one) are in flight in registers while the current
+// chunk is normalised and written, so every CTA always has a full chunk outstanding.
+constexpr int kLoadThreads = 128;
+constexpr int kLoadBatch = 8;  // 16-byte loads per thread and batch
+
+template <typename CT>
+__global__ void __launch_bounds__(kLoadThreads, 3)
+stream_load_kernel(const CT* __restrict__ y, CT* __restrict__ z, const double* __restrict__ aff_src,
+                   double* __restrict__ aff_dst, int F, int T, int D, int K, int rows, int SF, int nchunks,
+                   int* __restrict__ dead, int* __restrict__ flags, int* __restrict__ next_bin) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(smem_raw);  // [SF][D + 1]
+  __shared__ int s_bin[2];
+  const int ldt = D + 1;
+  const int tid = threadIdx.x;
+  const int per_chunk = SF * D;                                   // complex elements of a full chunk
+  const int nbatch = (per_chunk + kLoadThreads * kLoadBatch - 1) / (kLoadThreads * kLoadBatch);
+  // the first batch of a chunk travels in registers across the pipeline; chunks with more than
+  // one batch (D > 8) load the rest synchronously
+  auto load_batch = [&](int f, int c, int b, double2 (&v)[kLoadBatch]) {
+    const int t0 = c * SF;
+    const int n = max(0, min(SF, T - t0)) * D;
+    const CT* __restrict__ yf = y + ((size_t)f * T + t0) * D;
+#pragma unroll
+    for (int j = 0; j < kLoadBatch; ++j) {
+      const int i = (b * kLoadBatch + j) * kLoadThreads + tid;
+      if (i < n) v[j] = ld_cplx(yf + i);
+    }
+  };
+  auto store_batch = [&](int c, int b, const double2 (&v)[kLoadBatch]) {
+    const int n = max(0, min(SF, T - c * SF)) * D;
+#pragma unroll
+    for (int j = 0; j < kLoadBatch; ++j) {
+      const int i = (b * kLoadBatch + j) * kLoadThreads + tid;
+      if (i < n) {
+        const int tt = i / D, d = i - tt * D;
+        tile[tt * ldt + d] = v[j];
+      }
+    }
+  };
+  if (tid == 0) {
+    s_bin[0] = atomicAdd(next_bin, 1);
+    s_bin[1] = atomicAdd(next_bin, 1);
+  }
+  __syncthreads();
+  int f = s_bin[0], nf = s_bin[1];
+  double2 v[kLoadBatch];
+  if (f < F) load_batch(f, 0, 0, v);
+  while (f < F) {
+    bool zero_frame = false;
+    for (int c = 0; c < nchunks; ++c) {
+      const int t0 = c * SF;
+      const int nt = max(0, min(SF, T - t0));
+      store_batch(c, 0, v);
+      for (int b = 1; b < nbatch; ++b) {
+        double2 u[kLoadBatch];
+        load_batch(f, c, b, u);
+        store_batch(c, b, u);
+      }
+      // next chunk of this bin, or the first chunk of the next bin: in flight from here on
+      if (c + 1 < nchunks) load_batch(f, c + 1, 0, v);
+      else if (nf < F) load_batch(nf, 0, 0, v);
+      __syncthreads();
+      for (int tt = tid; tt < nt; tt += kLoadThreads) {
+        double n2 = 0.0;
+        for (int d = 0; d < D; ++d) {
+          const double2 x = tile[tt * ldt + d];
+          n2 += x.x * x.x + x.y * x.y;
+        }
+        double nrm = sqrt(n2);
+        zero_frame |= nrm == 0.0;
+        if (nrm == 0.0) nrm = kTiny;
+        nrm = fmax(nrm, kTiny);
+        for (int d = 0; d < D; ++d) {
+          double2 x = tile[tt * ldt + d];
+          x.x = x.x / nrm; x.y = x.y / nrm;
+          tile[tt * ldt + d] = x;
+        }
+      }
+      __syncthreads();
+      CT* __restrict__ zc = z + ((size_t)f * nchunks + c) * rows * SF;
+      for (int i = tid; i < rows * SF; i += kLoadThreads) {
+        const int r = i / SF, tt = i - r * SF;
+        double2 x = make_double2(0.0, 0.0);
+        if (tt < nt) x = tile[tt * ldt + row_channel(D, r)];
+        st_cplx(zc + i, x.x, x.y);
+      }
+      __syncthreads();
+    }
+    if (aff_dst != nullptr) {
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(aff_src + (size_t)f * K * T);
+      double2* __restrict__ dst = reinterpret_cast<double2*>(aff_dst + (size_t)f * K * T);
+      const int n = K * T;
+      if (((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(dst)) & 15) == 0) {  // vector copies
+        for (int i0 = 0; i0 < n / 2; i0 += kLoadThreads * kLoadBatch) {
+          double2 u[kLoadBatch];
+#pragma unroll
+          for (int j = 0; j < kLoadBatch; ++j) {
+            const int i = i0 + j * kLoadThreads + tid;
+            if (i < n / 2) u[j] = __ldg(src + i);
+          }
+#pragma unroll
+          for (int j = 0; j < kLoadBatch; ++j) {
+            const int i = i0 + j * kLoadThreads + tid;
+            if (i < n / 2) dst[i] = u[j];
+          }
+        }
+        if ((n & 1) && tid == 0) aff_dst[(size_t)f * K * T + n - 1] = __ldg(aff_src + (size_t)f * K * T + n - 1);
+      } else {
+        const double* __restrict__ s1 = aff_src + (size_t)f * K * T;
+        double* __restrict__ d1 = aff_dst + (size_t)f * K * T;
+        for (int i0 = 0; i0 < n; i0 += kLoadThreads * kLoadBatch) {
+          double u[kLoadBatch];
+#pragma unroll
+          for (int j = 0; j < kLoadBatch; ++j) {
+            const int i = i0 + j * kLoadThreads + tid;
+            if (i < n) u[j] = __ldg(s1 + i);
+          }
+#pragma unroll
+          for (int j = 0; j < kLoadBatch; ++j) {
+            const int i = i0 + j * kLoadThreads + tid;
+            if (i < n) d1[i] = u[j];
+          }
+        }
+      }
+    }
+    if (zero_frame && dead != nullptr) dead[f] = 1;
+    if (tid == 0) s_bin[0] = atomicAdd(next_bin, 1);  // the bin after next
+    __syncthreads();  // every thread's stores of this bin are ordered before the release below
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + f), "r"(0) : "memory");
+    f = nf;
+    nf = s_bin[0];
+    __syncthreads();  // s_bin[0] is rewritten at the end of the next bin
+  }
+}
+
 }  // namespace pbb

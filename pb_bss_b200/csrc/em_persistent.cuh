@@ -67,6 +67,9 @@ struct PersistArgs {
   const int* dead;  // (F) bin has an all-zero observation frame (set by normalize_staged_kernel)
   int* status;
   CwSpline spline;  // complex Watson only: inverse hypergeometric ratio (model_kind 1)
+  int wave_c;      // task order: 0 = iteration-major; c > 0 = rounds, c bins join per round (decode_ticket)
+  int wait_load;   // streamed upload: the bin's first task waits for flags[bin] >= 0 (stream_load_kernel)
+  const int* order;  // optional explicit task order: order[ticket] = bin | iteration << 16 (host-built, api_cacgmm.cu)
   unsigned long long* phase;  // debug: per-phase cycle sums (PBB_PHASE_TIMING builds)
 };
 
@@ -121,6 +124,39 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// ---- task order ------------------------------------------------------------------
+// wave_c == 0: iteration-major, ticket = it * F + bin.
+// wave_c = c > 0 (streamed upload): the bins arrive over PCIe in ascending order while the
+// kernel runs, so they join the schedule c at a time, one group per round, and every round
+// advances all joined bins by one iteration: round r holds (bin b, iteration r - b / c) for
+// b in [min(F, c max(0, r - I + 1)), min(F, c (r + 1))).  Bins that arrived early run ahead
+// instead of every CTA queueing behind the link.  Tickets before round r:
+// H(r) - H(max(0, r - I)) with H(r) = sum_{j < r} min(F, c (j + 1)).  A task still only
+// depends on a lower ticket ((b, it - 1) is one round earlier).
+__device__ __forceinline__ long long wave_h(long long r, int F, int c) {
+  const long long m = F / c;
+  const long long n = r < m ? r : m;
+  return (long long)c * n * (n + 1) / 2 + (r - n) * (long long)F;
+}
+__device__ __forceinline__ long long wave_prefix(int r, int F, int I, int c) {
+  return wave_h(r, F, c) - wave_h(r > I ? r - I : 0, F, c);
+}
+__device__ __forceinline__ void decode_ticket(int t, int F, int I, int c, int& bin, int& it) {
+  if (c == 0) {
+    it = t / F;
+    bin = t - it * F;
+    return;
+  }
+  int lo = 0, hi = I + (F + c - 1) / c - 1;  // last round r with wave_prefix(r) <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (wave_prefix(mid, F, I, c) <= (long long)t) lo = mid; else hi = mid;
+  }
+  const long long first = (long long)c * (lo - I + 1 > 0 ? lo - I + 1 : 0);
+  bin = (int)(first < F ? first : F) + (int)(t - wave_prefix(lo, F, I, c));
+  it = lo - bin / c;
+}
+
 __device__ __forceinline__ double2 lds_cplx(const double2* p) { return *p; }
 __device__ __forceinline__ double2 lds_cplx(const float2* p) {
   const float2 v = *p;
@@ -148,7 +184,7 @@ struct PersistSmem {
   alignas(16) double raw[2][8];  // lean variant: published (sum gamma_k, ld_k), padded to 4 + 4, cp.async target
   uint64_t full[kStages];
   int tab[NS];
-  int tick[2];
+  int tick[4];            // [0] first ticket; [1..3] next ticket, its bin, its iteration
   int ready;              // the next task's model was already published when probed
 };
 
@@ -501,7 +537,7 @@ __device__ __forceinline__ void general_chunk(const PersistArgs& a, PersistSmem<
     if (!done) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        gam[k] = a.aff_in[((size_t)bin * K + k) * T + tc];
+        gam[k] = __ldcg(a.aff_in + ((size_t)bin * K + k) * T + tc);  // L2: may just have been streamed in
         invq[k] = 1.0;
       }
     }
@@ -590,6 +626,16 @@ em_persistent_kernel(const PersistArgs a) {
   }
   __syncthreads();
   int cur = sm.tick[0];
+  int bin = 0, it = 0;
+  if (cur < total) {
+    if (a.order != nullptr) {
+      const int v = __ldcg(a.order + cur);
+      bin = v & 0xffff;
+      it = v >> 16;
+    } else {
+      decode_ticket(cur, F, a.iterations, a.wave_c, bin, it);
+    }
+  }
   unsigned chunk_cnt = 0;  // chunks consumed so far by this CTA (ring position)
 
   // One 1-D TMA bulk copy per ring stage: the staged layout keeps the ROWS x kStageFrames block
@@ -603,7 +649,9 @@ em_persistent_kernel(const PersistArgs a) {
                &sm.full[st]);
     }
   };
-  if (g == 0 && cur < total) issue_chunk(cur % F, 0, 0);
+  // streamed upload: a bin's observation may not have arrived yet; its first task issues its own
+  // first chunk after the arrival flag instead of having it prefetched
+  if (g == 0 && cur < total && !(a.wait_load && it == 0)) issue_chunk(bin, 0, 0);
 
 #ifdef PBB_PHASE_TIMING
   long long _tp = clock64();
@@ -613,11 +661,23 @@ em_persistent_kernel(const PersistArgs a) {
   int cb = 0;
   bool pf = false;
   while (cur < total) {
-    const int it = cur / F, bin = cur - it * F;
     const bool mstep_only = a.first_is_m && it == 0;
     const bool last_it = it == a.iterations - 1;
-    int tnext = 0;
-    if (tid == 0) tnext = atomicAdd(a.ticket, 1);  // the task after this one; consumed a chunk later
+    int tnext = 0, nbin = 0, nit = 0;  // the task after this one (thread 0; decoded a chunk later)
+    int oraw = 0;                      // its entry of the explicit order table, in flight
+    if (tid == 0) tnext = atomicAdd(a.ticket, 1);
+    if (a.wait_load && it == 0) {
+      if (tid == 0) {
+        while (ld_acquire_gpu(a.flags + bin) < 0) __nanosleep(200);
+      }
+      __syncthreads();
+      if (g == 0) {
+        // the staged rows were written with ordinary stores by another CTA: order them before
+        // this CTA's async-proxy (TMA) read
+        asm volatile("fence.proxy.async;" ::: "memory");
+        issue_chunk(bin, 0, chunk_cnt);
+      }
+    }
     if (!mstep_only && !pf) {
       if (tid == 0) {
         while (ld_acquire_gpu(a.flags + bin) < it) __nanosleep(40);
@@ -683,12 +743,21 @@ em_persistent_kernel(const PersistArgs a) {
       if (tid == 0) {
         const int c_probe = nchunks >= 3 ? nchunks - 3 : -1;
         const int c_pub = nchunks >= 2 ? nchunks - 2 : 0;
-        if (c == c_probe && !FULL && tnext < total) {
-          const int ni = tnext / F, nb = tnext - ni * F;
-          probe = (a.first_is_m && ni == 0) ? -1 : ld_acquire_gpu(a.flags + nb) - ni;  // >= 0: published
+        if (a.order != nullptr) {
+          // explicit order: ticket (atomic, task start) -> table entry (issued here) -> decoded one chunk
+          // top later; no flag probe / model prefetch in this mode
+          if (c == (c_probe >= 0 ? c_probe : c_pub) && tnext < total) oraw = __ldcg(a.order + tnext);
+          if (c == c_pub) { nbin = oraw & 0xffff; nit = oraw >> 16; }
+        } else if (c == (c_probe >= 0 ? c_probe : c_pub) && tnext < total) {
+          decode_ticket(tnext, F, a.iterations, a.wave_c, nbin, nit);
+        }
+        if (c == c_probe && !FULL && tnext < total && a.order == nullptr) {
+          probe = (a.first_is_m && nit == 0) ? -1 : ld_acquire_gpu(a.flags + nbin) - nit;  // >= 0: published
         }
         if (c == c_pub) {
           sm.tick[1] = tnext;
+          sm.tick[2] = nbin;
+          sm.tick[3] = nit;
           sm.ready = (!FULL && MODEL == 0 && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
         }
       }
@@ -697,13 +766,14 @@ em_persistent_kernel(const PersistArgs a) {
           issue_chunk(bin, c + 1, chunk_cnt + 1);
         } else {
           const int nx = __shfl_sync(0xffffffffu, tnext, 0);
-          if (nx < total) issue_chunk(nx % F, 0, chunk_cnt + 1);
+          const int nxb = __shfl_sync(0xffffffffu, nbin, 0), nxi = __shfl_sync(0xffffffffu, nit, 0);
+          if (nx < total && !(a.wait_load && nxi == 0)) issue_chunk(nxb, 0, chunk_cnt + 1);
         }
       }
       if (!FULL && lean && last_chunk && nchunks >= 3 && sm.ready) {
         // prefetch the next task's model into the other buffer (16-byte L2 -> smem copies)
         pf_next = true;
-        const int nb = sm.tick[1] % F;
+        const int nb = sm.tick[2];
         const char* __restrict__ src = reinterpret_cast<const char*>(a.coef + (size_t)nb * K * NS);
         char* dst = reinterpret_cast<char*>(&sm.coef[cb ^ 1][0][0]);
         for (int i = tid; i < K * NS / 2; i += blockDim.x)
@@ -857,7 +927,7 @@ em_persistent_kernel(const PersistArgs a) {
         // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
         // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
         const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
-                              (a.dead == nullptr || a.dead[bin] == 0);
+                              (a.dead == nullptr || __ldcg(a.dead + bin) == 0);
         double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
         if (__any_sync(0xffffffffu, bad)) {
           if (lane == 0) atomicMax(a.status, bin + 1);
@@ -932,6 +1002,8 @@ em_persistent_kernel(const PersistArgs a) {
     }
     // all threads read the next ticket (published one chunk before the end of the pass)
     cur = sm.tick[1];
+    bin = sm.tick[2];
+    it = sm.tick[3];
     pf = pf_next;
     if (pf_next) cb ^= 1;
     // no barrier needed here: tick / ld / S are next written behind later barriers of the next task

@@ -1,4 +1,5 @@
 #include <atomic>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -79,6 +80,17 @@ int pbb_profile_dominant(char* name, int name_len, double* total_ms, int* launch
   if (launches) *launches = best_n;
   clear_locked();
   return (int)acc.size();
+}
+
+// Prints every recorded launch (name, device ms) to stderr in launch order; keeps the records.
+void pbb_profile_dump(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    fprintf(stderr, "[pbb] %-32s %9.4f ms\n", r.name.c_str(), (double)ms);
+  }
 }
 
 }  // extern "C"

@@ -153,6 +153,7 @@ class CACGMMTrainer:
             inline_permutation_aligner=None,
             frames_per_block=0,
             multi_kernel=False,
+            streamed_upload=True,
             total_bins=None,
             bin_group=None,
     ):
@@ -170,6 +171,9 @@ class CACGMMTrainer:
             frames_per_block: tuning knob of the multi-kernel EM path (0 = default).
             multi_kernel: force the one-kernel-pair-per-iteration path instead
                 of the persistent kernel (A/B testing; same results).
+            streamed_upload: with ``y`` / ``initialization`` in pinned host memory (CPU
+                tensors after ``.pin_memory()``) the upload overlaps the EM iterations;
+                False reads them in one pass before the EM kernel starts (A/B testing).
             total_bins, bin_group: bin-sharded multi-GPU use (pb_bss_b200.parallel):
                 ``y`` holds this rank's contiguous slice of ``total_bins`` bins.  Only
                 the couplings across bins (frequency-tied weights, inline alignment)
@@ -182,7 +186,11 @@ class CACGMMTrainer:
             f'{initialization is None} xor {num_classes is None}')
         assert covariance_norm in _NORMS, covariance_norm
         like_numpy = not _device.is_tensor(y)
-        yd = _device.to_device(y)
+        weight_mode_probe = _weight_mode(weight_constant_axis, y.ndim)
+        coupled = inline_permutation_aligner is not None or weight_mode_probe in (
+            _lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED)
+        # pinned host tensors stay where they are: pbb_cacgmm_fit streams them in while it computes
+        yd = _device.to_device(y, keep_pinned=not coupled)
         assert yd.is_complex(), yd.dtype
         assert yd.shape[-1] > 1, yd.shape
         assert iterations > 0, iterations
@@ -207,7 +215,7 @@ class CACGMMTrainer:
             shape = (*independent, K, N)
             assert initialization.ndim == len(shape), (initialization.shape, shape)
             assert tuple(initialization.shape[-2:]) == shape[-2:], (initialization.shape, shape)
-            init_dev = _device.to_device(initialization, torch.float64)
+            init_dev = _device.to_device(initialization, torch.float64, keep_pinned=yd.device.type == 'cpu')
             init_dev = init_dev.expand(shape).reshape(F, K, N).contiguous()
         else:
             raise TypeError('No sufficient initialization.')
@@ -239,6 +247,11 @@ class CACGMMTrainer:
             V, lam, w, _, wm_in = model_in._device_model(independent, F)
             assert wm_in == _lib.WEIGHT_TIME, 'warm start with frequency-tied weights goes through the coupled loop'
             V, lam, w = V.clone(), lam.clone(), w.clone()
+        elif yd.device.type == 'cpu':
+            # pinned observation in, pinned model out: the final update kernel writes it over PCIe
+            V = torch.empty((F, K, D, D), dtype=torch.complex128, pin_memory=True)
+            lam = torch.empty((F, K, D), dtype=torch.float64, pin_memory=True)
+            w = torch.empty((F, K), dtype=torch.float64, pin_memory=True)
         else:
             V = _device.empty((F, K, D, D), torch.complex128)
             lam = _device.empty((F, K, D), torch.float64)
@@ -250,7 +263,7 @@ class CACGMMTrainer:
             affiliation_eps=float(affiliation_eps),
             eigenvalue_floor=float(eigenvalue_floor),
             frames_per_block=int(frames_per_block),
-            reserved=1 if multi_kernel else 0)
+            reserved=(1 if multi_kernel else 0) | (0 if streamed_upload else 2))
         lib = _lib.load()
         nbytes = lib.pbb_cacgmm_workspace_bytes(F, N, D, K)
         ws = _device.workspace(nbytes)

@@ -325,6 +325,38 @@ def test_inline_permutation_alignment_matches_reference_golden():
         CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=2, inline_permutation_aligner=al)
 
 
+@pytest.mark.parametrize('shape', [(129, 200, 4, 2, 20), (40, 333, 8, 3, 12), (7, 130, 6, 4, 5)])
+@pytest.mark.parametrize('cdtype', ['complex128', 'complex64'])
+def test_pinned_host_inputs_stream_in_and_match_device_inputs(shape, cdtype):
+    """y / initialization in pinned host memory are read in place over PCIe by a loader kernel that
+    overlaps the EM kernel (wave task order).  Every task computes exactly what it computes with
+    device-resident inputs, so the models must be bit-identical."""
+    import torch
+    from pb_bss_b200.distribution import CACGMMTrainer
+    F, T, D, K, iters = shape
+    y, _ = synth.structured_stft(F, T, D, K, seed=3)
+    y[2, 5] = 0  # an all-zero frame: that bin takes the reference-normalisation path
+    y = y.astype(cdtype)
+    init = synth.init_affiliation(F, K, T, seed=7)
+    y_pin, init_pin = torch.from_numpy(y).pin_memory(), torch.from_numpy(init).pin_memory()
+    ref = CACGMMTrainer().fit(y_pin.cuda(), initialization=init_pin.cuda(), iterations=iters)
+    for kw in ({}, {'streamed_upload': False}):
+        got = CACGMMTrainer().fit(y_pin, initialization=init_pin, iterations=iters, **kw)
+        # pinned observation in -> the model is written to pinned host memory as well
+        assert not got.weight.is_cuda and got.weight.is_pinned()
+        assert torch.equal(got.weight, ref.weight.cpu()), kw
+        assert torch.equal(got.cacg.covariance_eigenvalues, ref.cacg.covariance_eigenvalues.cpu()), kw
+        assert torch.equal(got.cacg.covariance_eigenvectors, ref.cacg.covariance_eigenvectors.cpu()), kw
+    # pinned observation, device initialisation; and a warm start from pinned memory
+    got = CACGMMTrainer().fit(y_pin, initialization=init_pin.cuda(), iterations=iters)
+    assert torch.equal(got.cacg.covariance_eigenvalues, ref.cacg.covariance_eigenvalues.cpu())
+    warm_dev = CACGMMTrainer().fit(y_pin.cuda(), initialization=ref, iterations=2)
+    warm_pin = CACGMMTrainer().fit(y_pin, initialization=ref, iterations=2)
+    assert torch.equal(warm_pin.cacg.covariance_eigenvalues.cpu(), warm_dev.cacg.covariance_eigenvalues.cpu())
+    # the model fitted from pinned memory predicts like any other
+    np.testing.assert_array_equal(got.predict(y_pin.cuda()).cpu().numpy(), ref.predict(y_pin.cuda()).cpu().numpy())
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
