@@ -10,6 +10,7 @@
 
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
+#include "em_ws.cuh"
 #include "prof.cuh"
 
 #ifndef PBB_CTA_FPL
@@ -385,6 +386,14 @@ static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
   if (full)
     return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, 32 * (D / 2),
                                      sizeof(PersistSmem<D, K, CT>), &cache_full, a, "em_persistent_kernel", st);
+  if constexpr (D == 8) {
+    // warp-specialised variant (em_ws.cuh): producer / EM / update warps with their own register budgets
+    static int cache_ws = 0;
+    static const bool no_ws = getenv("PBB_NO_WS") != nullptr;  // A/B switch
+    if (!no_ws)
+      return launch_persistent_generic(em_ws_kernel<K, CT>, 256, sizeof(WsSmem<D, K, CT>), &cache_ws, a,
+                                       "em_ws_kernel", st);
+  }
   return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL>, 32 * (D / 2),
                                    sizeof(PersistSmem<D, K, CT>), &cache_lean, a, "em_persistent_kernel", st);
 }

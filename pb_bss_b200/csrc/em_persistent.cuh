@@ -302,8 +302,16 @@ __device__ __forceinline__ void softmax_watson(const double (&q)[K], const doubl
 // channels are rows 2g .. 2g+NLOC-1, i.e. one base register plus immediates.
 // No per-frame masking: padded frames have z = 0, add nothing to the scatter
 // sums, and their gamma is subtracted analytically by the caller.
-template <int D, int K, typename CT, int MODEL>
-__device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps, int lane,
+// exchange barrier of the E-step: the whole CTA, or (NAMED) only the D/2 slot-group warps of a
+// warp-specialised CTA (em_ws.cuh), which meet on named barrier 1
+template <int D, bool NAMED>
+__device__ __forceinline__ void em_exchange_barrier() {
+  if constexpr (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(32 * (D / 2)) : "memory");
+  else __syncthreads();
+}
+
+template <int D, int K, typename CT, int MODEL, bool NAMED = false, typename SMT>
+__device__ __forceinline__ void lean_chunk(SMT& sm, int cb, int g, int st, int nsteps, int lane,
                                            int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
                                            double (&sg)[K], int j0 = 0) {
   using G = GroupDims<D>;
@@ -333,7 +341,7 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, in
     double* __restrict__ xw = &sm.xq[buf][g][0][lane];
 #pragma unroll
     for (int k = 0; k < K; ++k) xw[k * 32] = p0[k] + p1[k];
-    __syncthreads();
+    em_exchange_barrier<D, NAMED>();
     const double* __restrict__ xr = &sm.xq[buf][0][0][lane];
     double q[K];
 #pragma unroll
@@ -360,8 +368,8 @@ __device__ __forceinline__ void lean_chunk(PersistSmem<D, K, CT>& sm, int cb, in
 // the coefficient loads, the barrier and the loop overhead are shared by the two
 // frames, and their E-step / softmax dependency chains interleave, which is what
 // keeps the fp64 pipe busy with only two warps per scheduler.
-template <int D, int K, typename CT, int MODEL>
-__device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int cb, int g, int st, int nsteps2, int lane,
+template <int D, int K, typename CT, int MODEL, bool NAMED = false, typename SMT>
+__device__ __forceinline__ void lean_chunk2(SMT& sm, int cb, int g, int st, int nsteps2, int lane,
                                             int& buf, double eps, double (&acc)[K * GroupDims<D>::NSG],
                                             double (&sg)[K]) {
   using G = GroupDims<D>;
@@ -400,7 +408,7 @@ __device__ __forceinline__ void lean_chunk2(PersistSmem<D, K, CT>& sm, int cb, i
       xw[k * 32] = pA0[k] + pA1[k];
       xw[(K + k) * 32] = pB0[k] + pB1[k];
     }
-    __syncthreads();
+    em_exchange_barrier<D, NAMED>();
     const double* __restrict__ xr = &sm.xq[buf][0][0][lane];
     double qA[K], qB[K];
 #pragma unroll
@@ -477,8 +485,8 @@ __device__ __forceinline__ void softmax_general(const double (&q)[K], const doub
 // General step (runtime group index): M-step-only iteration 0, and the FULL
 // variant (saliency, source activity mask, log-domain softmax).  Frames are
 // masked individually.
-template <int D, int K, typename CT, bool FULL>
-__device__ __forceinline__ void general_chunk(const PersistArgs& a, PersistSmem<D, K, CT>& sm, int g, int bin,
+template <int D, int K, typename CT, bool FULL, typename SMT>
+__device__ __forceinline__ void general_chunk(const PersistArgs& a, SMT& sm, int g, int bin,
                                               int st, int t_chunk, int nsteps, int lane, int& buf, bool mstep_only,
                                               bool fast, double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K]) {
   using G = GroupDims<D>;
@@ -602,6 +610,94 @@ __device__ __forceinline__ double warp_hpd_inverse(double2* __restrict__ A, int 
   }
   *ok = good;
   return det;
+}
+
+// Model update of one (bin, class) by one warp (cACGMM): scatter sums Sk[0..NS) + sum of gamma
+// Sk[NS] -> E-step coefficients in a.coef (+ the published scalars), see the file header.
+// A, V: D x D shared-memory scratch of the warp; lamk: D doubles.
+template <int D, bool FULL>
+__device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin, int k, int K, int lane,
+                                                  double2* __restrict__ A, double2* __restrict__ V,
+                                                  double* __restrict__ lamk, const double* __restrict__ Sk,
+                                                  const int* __restrict__ tab, double* __restrict__ ld_out) {
+  constexpr int NS = D * D;
+  double* Ad = reinterpret_cast<double*>(A);
+    const double scale = (double)D / fmax(Sk[NS], kTiny);
+    bool bad = false;
+    auto build = [&]() {
+      for (int s = lane; s < NS; s += 32) {
+        const int pk = tab[s];
+        const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
+        const double v = Sk[s] * scale;
+        bad |= !isfinite(v);
+        if (kind == 0) { Ad[2 * (d * D + d)] = v; Ad[2 * (d * D + d) + 1] = 0.0; }
+        else if (kind == 1) { Ad[2 * (d * D + e)] = v; Ad[2 * (e * D + d)] = v; }
+        else { Ad[2 * (d * D + e) + 1] = -v; Ad[2 * (e * D + d) + 1] = v; }
+      }
+      __syncwarp();
+    };
+    build();
+    // trace-normalise to tr = D: keeps all classes on a comparable scale
+    double tr = 0.0;
+    for (int d = lane; d < D; d += 32) tr += A[d * D + d].x;
+    tr = warp_sum(tr);
+    // covariance_norm=False keeps the reference's absolute scale (it survives into the returned
+    // eigenvalues); otherwise the scale is free and tr = D keeps all classes comparable
+    const double tn = a.covariance_norm == PBB_NORM_NONE ? 1.0 : (double)D / fmax(tr, kTiny);
+    for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
+    __syncwarp();
+    bool ok;
+    const double det = warp_hpd_inverse<D>(A, lane, &ok);
+    double ldk = log(det);
+    double tinv = 0.0;
+    for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
+    tinv = warp_sum(tinv);
+    // lambda_min / lambda_max >= 1 / (tr(A) tr(A^-1))
+    // A bin with an all-zero frame must keep the reference's own normalisation: such a frame has
+    // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
+    // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
+    const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
+                          (a.dead == nullptr || __ldcg(a.dead + bin) == 0);
+    double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
+    if (__any_sync(0xffffffffu, bad)) {
+      if (lane == 0) atomicMax(a.status, bin + 1);
+    }
+    if (no_floor) {
+      for (int s = lane; s < NS; s += 32) {
+        const int pk = tab[s];
+        const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
+        const double2 u = A[d * D + e], v = A[e * D + d];
+        co[s] = kind == 0 ? u.x : (kind == 1 ? (u.x + v.x) : -(u.y - v.y));
+      }
+    } else {
+      // reference semantics: eigendecomposition, normalise, floor (cacg.py:95-126)
+      build();
+      if (a.covariance_norm == PBB_NORM_TRACE) {
+        for (int i = lane; i < NS; i += 32) { A[i].x *= tn / D; A[i].y *= tn / D; }
+        __syncwarp();
+      }
+      warp_jacobi_small<D>(A, V, lane);
+      double lmax = -INFINITY;
+      for (int d = lane; d < D; d += 32) lmax = fmax(lmax, A[d * D + d].x);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+      for (int d = lane; d < D; d += 32) {
+        double l = A[d * D + d].x;
+        if (a.covariance_norm == PBB_NORM_EIGENVALUE) l = fmax(l / fmax(lmax, kTiny), a.eigenvalue_floor);
+        else l = fmax(l, lmax * a.eigenvalue_floor);
+        if (!isfinite(l)) atomicMax(a.status, bin + 1);
+        lamk[d] = l;
+      }
+      __syncwarp();
+      ldk = model_from_eig_warp(V, lamk, tab, D, lane, co);
+    }
+    if (lane == 0) {
+      *ld_out = ldk;
+      if (!FULL) {
+        a.ld[(size_t)bin * 4 + k] = ldk;
+        a.ew[(size_t)bin * 4 + k] = Sk[NS];
+      }
+    }
 }
 
 template <int D, int K, typename CT, bool FULL, int FPL, int MODEL = 0>
@@ -892,82 +988,7 @@ em_persistent_kernel(const PersistArgs a) {
           }
           continue;
         }
-        const double scale = (double)D / fmax(sm.S[k][NS], kTiny);
-        bool bad = false;
-        auto build = [&]() {
-          for (int s = lane; s < NS; s += 32) {
-            const int pk = sm.tab[s];
-            const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
-            const double v = sm.S[k][s] * scale;
-            bad |= !isfinite(v);
-            if (kind == 0) { Ad[2 * (d * D + d)] = v; Ad[2 * (d * D + d) + 1] = 0.0; }
-            else if (kind == 1) { Ad[2 * (d * D + e)] = v; Ad[2 * (e * D + d)] = v; }
-            else { Ad[2 * (d * D + e) + 1] = -v; Ad[2 * (e * D + d) + 1] = v; }
-          }
-          __syncwarp();
-        };
-        build();
-        // trace-normalise to tr = D: keeps all classes on a comparable scale
-        double tr = 0.0;
-        for (int d = lane; d < D; d += 32) tr += A[d * D + d].x;
-        tr = warp_sum(tr);
-        // covariance_norm=False keeps the reference's absolute scale (it survives into the returned
-        // eigenvalues); otherwise the scale is free and tr = D keeps all classes comparable
-        const double tn = a.covariance_norm == PBB_NORM_NONE ? 1.0 : (double)D / fmax(tr, kTiny);
-        for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
-        __syncwarp();
-        bool ok;
-        const double det = warp_hpd_inverse<D>(A, lane, &ok);
-        double ldk = log(det);
-        double tinv = 0.0;
-        for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
-        tinv = warp_sum(tinv);
-        // lambda_min / lambda_max >= 1 / (tr(A) tr(A^-1))
-        // A bin with an all-zero frame must keep the reference's own normalisation: such a frame has
-        // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
-        // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
-        const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
-                              (a.dead == nullptr || __ldcg(a.dead + bin) == 0);
-        double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
-        if (__any_sync(0xffffffffu, bad)) {
-          if (lane == 0) atomicMax(a.status, bin + 1);
-        }
-        if (no_floor) {
-          for (int s = lane; s < NS; s += 32) {
-            const int pk = sm.tab[s];
-            const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
-            const double2 u = A[d * D + e], v = A[e * D + d];
-            co[s] = kind == 0 ? u.x : (kind == 1 ? (u.x + v.x) : -(u.y - v.y));
-          }
-        } else {
-          // reference semantics: eigendecomposition, normalise, floor (cacg.py:95-126)
-          build();
-          if (a.covariance_norm == PBB_NORM_TRACE) {
-            for (int i = lane; i < NS; i += 32) { A[i].x *= tn / D; A[i].y *= tn / D; }
-            __syncwarp();
-          }
-          warp_jacobi_small<D>(A, sm.V[k], lane);
-          double lmax = -INFINITY;
-          for (int d = lane; d < D; d += 32) lmax = fmax(lmax, A[d * D + d].x);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-          for (int d = lane; d < D; d += 32) {
-            double l = A[d * D + d].x;
-            if (a.covariance_norm == PBB_NORM_EIGENVALUE) l = fmax(l / fmax(lmax, kTiny), a.eigenvalue_floor);
-            else l = fmax(l, lmax * a.eigenvalue_floor);
-            if (!isfinite(l)) atomicMax(a.status, bin + 1);
-            sm.lam[k][d] = l;
-          }
-          __syncwarp();
-          ldk = model_from_eig_warp(sm.V[k], sm.lam[k], sm.tab, D, lane, co);
-        }
-        if (lane == 0) {
-          sm.ld[k] = ldk;
-          if (!FULL) {
-            a.ld[(size_t)bin * 4 + k] = ldk;
-            a.ew[(size_t)bin * 4 + k] = sm.S[k][NS];
-          }
-        }
+        cacg_update_class<D, FULL>(a, bin, k, K, lane, A, sm.V[k], sm.lam[k], sm.S[k], sm.tab, &sm.ld[k]);
       }
       __syncthreads();
       PBB_PH(5);  // update (Gauss-Jordan)
