@@ -645,7 +645,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
       cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
       unsigned long long tot = 0;
       for (int i = 0; i < 8; ++i) tot += ph[i];
-      static const char* nm[8] = {"ticket+flag", "chunk-top", "tma-wait", "em-steps", "reduce", "update", "publish", "task-start"};
+      static const char* nm[8] = {"ticket+flag / model wait", "chunk-top / updater busy", "tma-wait", "em-steps", "reduce", "update / S wait", "publish / hand-over", "task-start / updater idle"};
       for (int i = 0; i < 8; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%\n", nm[i], 100.0 * ph[i] / (double)tot);
     }
 #endif

@@ -24,12 +24,37 @@
 
 namespace pbb {
 
+#ifndef PBB_WS_LEAD
+#define PBB_WS_LEAD 2  // chunks the EM warps have left when the producer takes the next ticket
+#endif
 constexpr int kWsStages = 3;
-constexpr int kWsEmRegs = 208;      // 128 threads x 208 + 128 threads x 48 = 32768 = 256 x 128
-constexpr int kWsHelperRegs = 48;
+#ifndef PBB_WS_EM_REGS
+#define PBB_WS_EM_REGS 208
+#endif
+constexpr int kWsEmRegs = PBB_WS_EM_REGS;  // 128 threads x 208 + 128 threads x 48 = 32768 = 256 x 128
+constexpr int kWsHelperRegs = 256 - PBB_WS_EM_REGS;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// mbarrier wait for the helper warps: they are latency tolerant, so they poll at a low rate
+// instead of competing with the EM warps of their scheduler for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
 }
 
 template <int D, int K, typename CT>
@@ -88,10 +113,14 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
     const int g = warp;
     unsigned chunk_cnt = 0;
     int buf = 0;
+#ifdef PBB_PHASE_TIMING
+    long long _tp = clock64();
+#endif
 #pragma unroll 1
     for (unsigned n = 0;; ++n) {
       const int mb = n & 1;
       mbar_wait(&sm.model_full[mb], (n >> 1) & 1u);
+      PBB_PH(0);  // wait for the staged model
       const int bin = sm.desc[mb][0], it = sm.desc[mb][1];
       if (bin < 0) {
         // no more tasks: tell the updaters
@@ -114,6 +143,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
       for (int c = 0; c < nchunks; ++c) {
         const int st = chunk_cnt % kWsStages;
         mbar_wait(&sm.full[st], (chunk_cnt / kWsStages) & 1u);
+        PBB_PH(2);  // TMA wait
         const int t_chunk = c * kStageFrames;
         const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
         if (!mstep_only) {
@@ -125,6 +155,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[st]);
         ++chunk_cnt;
+        PBB_PH(3);  // EM steps
       }
       if (!mstep_only && zs > T) {
         // the zs - T padded frames of every row behaved like zero observations
@@ -142,7 +173,9 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
       // ---- reduce the 32 frames of each warp; group g owns slots [g*NSG, (g+1)*NSG) ----
       warp_reduce_halving<K * NSG>(acc, lane);
       const int sb = n & 1;
+      PBB_PH(4);  // reduce
       mbar_wait(&sm.s_empty[sb], ((n >> 1) & 1u) ^ 1u);  // updaters are done with task n - 2
+      PBB_PH(5);  // wait for the S buffer
       {
         int lo, hi;
         reduce_range<K * NSG>(lane, lo, hi);
@@ -163,6 +196,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
       if (g == 0 && lane == 0) { sm.sdesc[sb][0] = bin; sm.sdesc[sb][1] = it; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_full[sb]);
+      PBB_PH(6);  // hand-over
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
@@ -187,16 +221,52 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
           }
         }
         const bool mstep_only = a.first_is_m && it == 0;
+        const bool late_z = mstep_only && a.wait_load;  // streamed upload: the bin may not have arrived yet
+        int issued = 0;  // chunks of this task already requested (lane 0)
+        auto issue_chunks = [&](int upto, bool blocking) {
+          // lane 0: request chunks [issued, upto) of this task; non-blocking stops at a busy stage
+          while (issued < upto) {
+            const int st = chunk_cnt % kWsStages;
+            const uint32_t par = ((chunk_cnt / kWsStages) & 1u) ^ 1u;
+            if (blocking) {
+              mbar_wait_relaxed(&sm.empty[st], par, 100);
+            } else {
+              uint32_t done;
+              asm volatile(
+                  "{\n"
+                  ".reg .pred p;\n"
+                  "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                  "selp.u32 %0, 1, 0, p;\n"
+                  "}\n"
+                  : "=r"(done)
+                  : "r"(smem_u32(&sm.empty[st])), "r"(par)
+                  : "memory");
+              if (!done) break;
+            }
+            mbar_expect_tx(&sm.full[st], kStageBytes);
+            bulk_g2s(&sm.zbuf[st][0][0], zbase + ((size_t)bin * nchunks + issued) * (SM::ROWS * kStageFrames),
+                     kStageBytes, &sm.full[st]);
+            ++chunk_cnt;
+            ++issued;
+          }
+        };
         if (bin >= 0 && lane == 0) {
+          // the observation does not depend on the model: request what fits into the ring right away, so
+          // that the copy overlaps the flag / model round trips below
+          if (!late_z) issue_chunks(nchunks, false);
           // dependency: the bin's previous iteration (or its arrival, streamed upload)
           if (mstep_only) {
             if (a.wait_load) while (ld_acquire_gpu(a.flags + bin) < 0) __nanosleep(200);
           } else {
-            while (ld_acquire_gpu(a.flags + bin) < it) __nanosleep(40);
+            while (ld_acquire_gpu(a.flags + bin) < it) {
+              issue_chunks(nchunks, false);  // keep the ring filled while the dependency is still executing
+              __nanosleep(40);
+            }
           }
+          if (late_z) asm volatile("fence.proxy.async;" ::: "memory");
         }
         __syncwarp();
-        mbar_wait(&sm.model_empty[mb], ((n >> 1) & 1u) ^ 1u);  // EM warps are done with task n - 2
+        mbar_wait_relaxed(&sm.model_empty[mb], ((n >> 1) & 1u) ^ 1u, 100);  // EM warps are done with task n - 2
         if (bin >= 0 && !mstep_only) {
           const double* __restrict__ cf = a.coef + (size_t)bin * K * NS;
           for (int i = lane; i < K * NS; i += 32) (&sm.coef[mb][0][0])[i] = __ldcg(cf + i);
@@ -216,25 +286,28 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         if (lane == 0) mbar_arrive(&sm.model_full[mb]);
         if (bin < 0) break;
         if (lane == 0) {
-          if (mstep_only && a.wait_load) asm volatile("fence.proxy.async;" ::: "memory");
-          for (int c = 0; c < nchunks; ++c) {
-            const int st = chunk_cnt % kWsStages;
-            mbar_wait(&sm.empty[st], ((chunk_cnt / kWsStages) & 1u) ^ 1u);
-            mbar_expect_tx(&sm.full[st], kStageBytes);
-            bulk_g2s(&sm.zbuf[st][0][0], zbase + ((size_t)bin * nchunks + c) * (SM::ROWS * kStageFrames), kStageBytes,
-                     &sm.full[st]);
-            ++chunk_cnt;
-          }
+          issue_chunks(nchunks, true);
+          // Do not take the next ticket too early: with two tickets per CTA in flight the grid holds
+          // more tasks than there are bins and most dependencies are still executing.  Wait until the
+          // EM warps have ~2 chunks left (enough to hide ticket, flag and model latency).
+          const unsigned x = chunk_cnt - (unsigned)(nchunks >= PBB_WS_LEAD + 1 ? PBB_WS_LEAD + 1 : nchunks);
+          mbar_wait_relaxed(&sm.empty[x % kWsStages], (x / kWsStages) & 1u, 100);
         }
         __syncwarp();
       }
     } else if (warp - M - 1 < NU) {
       // =============================== updaters ===============================
       const int u = warp - M - 1;
+#ifdef PBB_PHASE_TIMING
+      long long _tp = clock64();
+#undef PBB_PH
+#define PBB_PH(i) do { if (u == 0 && lane == 0) { long long _t = clock64(); atomicAdd(&a.phase[i], (unsigned long long)(_t - _tp)); _tp = _t; } } while (0)
+#endif
 #pragma unroll 1
       for (unsigned n = 0;; ++n) {
         const int sb = n & 1;
-        mbar_wait(&sm.s_full[sb], (n >> 1) & 1u);
+        mbar_wait_relaxed(&sm.s_full[sb], (n >> 1) & 1u, 100);
+        PBB_PH(7);  // updater idle
         const int bin = sm.sdesc[sb][0], it = sm.sdesc[sb][1];
         if (bin < 0) break;
         const bool last_it = it == a.iterations - 1;
@@ -253,6 +326,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
           asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
           if (u == 0 && lane == 0) st_release_gpu(a.flags + bin, it + 1);
         }
+        PBB_PH(1);  // updater busy
       }
     }
   }
