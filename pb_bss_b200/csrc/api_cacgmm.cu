@@ -8,6 +8,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
+
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
 #include "em_ws.cuh"
@@ -244,8 +246,8 @@ static int launch_from_eig(FromEigArgs u, cudaStream_t st) {
 }
 
 // ---- persistent kernel launch ---------------------------------------------------
-constexpr int kLoadReserve = 4;  // EM CTA slots left free in streamed-upload mode
-constexpr int kLoadCtas = 16;    // stream_load_kernel grid: <= 4 of its CTAs fit into one free EM slot
+constexpr int kLoadReserve = 4;  // EM CTA slots left free in streamed-upload mode (insurance, see launch_stream_load)
+constexpr int kLoadCtas = 16;    // stream_load_kernel grid
 
 // Task order of the streamed upload (em_persistent.cuh).  The bins arrive over PCIe in ascending
 // order, `arrive` per time slot; a slot is one task duration and the machine runs `cap` tasks per
@@ -318,9 +320,11 @@ static int classify_pointer(const void* p, const void** dev_alias, bool* is_host
 }
 
 // side stream + events for the upload that overlaps the EM kernel (one set per process)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct LoadStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  StreamWaitValue32Fn wait_value = nullptr;  // cuStreamWaitValue32, resolved through the runtime
   int device = -1;
 };
 static int get_load_stream(LoadStream** out) {
@@ -333,6 +337,12 @@ static int get_load_stream(LoadStream** out) {
     PBB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
     PBB_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
     PBB_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      l.wait_value = reinterpret_cast<StreamWaitValue32Fn>(fn);
+    (void)cudaGetLastError();
     l.device = dev;
   }
   *out = &l;
@@ -341,15 +351,17 @@ static int get_load_stream(LoadStream** out) {
 
 template <typename CT>
 static int launch_stream_load(const void* y, void* z, const double* aff_src, double* aff_dst, int F, int T, int D, int K,
-                              int* dead, int* flags, int* next_bin, cudaStream_t st) {
+                              int* dead, int* flags, int* next_bin, int* started, int* ctas_out, cudaStream_t st) {
   const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
   const size_t smem = (size_t)kStageFrames * (D + 1) * sizeof(double2);
   LaunchScope ls("stream_load_kernel", st);
   int ctas = kLoadCtas;
   if (const char* e = getenv("PBB_LOAD_CTAS")) ctas = atoi(e) > 0 ? atoi(e) : ctas;  // tuning override
-  stream_load_kernel<CT><<<ctas < F ? ctas : F, kLoadThreads, smem, st>>>(
+  ctas = ctas < F ? ctas : F;
+  *ctas_out = ctas;
+  stream_load_kernel<CT><<<ctas, kLoadThreads, smem, st>>>(
       reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), aff_src, aff_dst, F, T, D, K, stage_rows(D),
-      kStageFrames, nchunks, dead, flags, next_bin);
+      kStageFrames, nchunks, dead, flags, next_bin, started);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -549,11 +561,22 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     PBB_CUDA(cudaEventRecord(l->fork, st));
     PBB_CUDA(cudaStreamWaitEvent(l->stream, l->fork, 0));
     double* aff_dst = aff_host ? ws.aff_stage : nullptr;
+    int* next_bin = reinterpret_cast<int*>(ws.phase + 15);
+    int* started = reinterpret_cast<int*>(ws.phase + 14);
+    int ctas = 0;
     r = dtype == PBB_C128
-            ? launch_stream_load<double2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, reinterpret_cast<int*>(ws.phase + 15), l->stream)
-            : launch_stream_load<float2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, reinterpret_cast<int*>(ws.phase + 15), l->stream);
+            ? launch_stream_load<double2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, l->stream)
+            : launch_stream_load<float2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, l->stream);
     if (r) return r;
     PBB_CUDA(cudaEventRecord(l->join, l->stream));
+    // Hold the EM kernel back until every loader CTA runs: launched at the same moment, the EM grid
+    // could take the whole machine first and leave the loader only the reserved slots (it would still
+    // finish -- bins are handed out by a counter -- but at a fraction of the link rate).
+    if (l->wait_value != nullptr) {
+      if (l->wait_value(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(started), (cuuint32_t)ctas,
+                        CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        l->wait_value = nullptr;  // not supported here: rely on the reserved slots
+    }
     if (aff_host) init_aff = ws.aff_stage;
   } else if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
     r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)

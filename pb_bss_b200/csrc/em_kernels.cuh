@@ -950,16 +950,22 @@ __global__ void normalize_staged_kernel(const CT* __restrict__ y, CT* __restrict
 // 128-frame chunk (of this bin or the next one) are in flight in registers while the current
 // chunk is normalised and written, so every CTA always has a full chunk outstanding.
 constexpr int kLoadThreads = 128;
-constexpr int kLoadBatch = 8;  // 16-byte loads per thread and batch
+constexpr int kLoadBatch = 8;  // 16-byte loads per thread and batch: 16 KB per CTA in flight
 
 template <typename CT>
 __global__ void __launch_bounds__(kLoadThreads, 3)
 stream_load_kernel(const CT* __restrict__ y, CT* __restrict__ z, const double* __restrict__ aff_src,
                    double* __restrict__ aff_dst, int F, int T, int D, int K, int rows, int SF, int nchunks,
-                   int* __restrict__ dead, int* __restrict__ flags, int* __restrict__ next_bin) {
+                   int* __restrict__ dead, int* __restrict__ flags, int* __restrict__ next_bin,
+                   int* __restrict__ started) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* tile = reinterpret_cast<double2*>(smem_raw);  // [SF][D + 1]
   __shared__ int s_bin[2];
+  // the host holds the EM kernel's launch back until every loader CTA is resident (cuStreamWaitValue32)
+  if (threadIdx.x == 0) {
+    atomicAdd(started, 1);
+    __threadfence();
+  }
   const int ldt = D + 1;
   const int tid = threadIdx.x;
   const int per_chunk = SF * D;                                   // complex elements of a full chunk
