@@ -633,10 +633,11 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status;
     p.phase = ws.phase; p.dead = ws.dead;
     if (streamed) {
-      // bins joining per round ~ round duration / arrival time of one bin (em_persistent.cuh,
-      // decode_ticket): ~12 us rounds at D = 8, K = 3, T = 500 against ~50 GB/s of PCIe reads
+      // bins joining per slot ~ slot duration / arrival time of one bin at ~50 GB/s of PCIe reads
       const double bin_bytes = (double)T * D * (dtype == PBB_C128 ? 16.0 : 8.0) + (aff_host ? 8.0 * K * T : 0.0);
-      const double round_us = 12.0 * (T / 500.0) * (D * D / 64.0) * (K / 3.0);
+      // one slot of the order table = one link of a bin's dependency chain (task + update + staging
+      // of the next model, ~23 us at D = 8, K = 3, T = 500), during which the machine runs ~1.6 tasks per CTA
+      const double round_us = 23.0 * (T / 500.0) * (D * D / 64.0) * (K / 3.0);
       int c = (int)(round_us / (bin_bytes / 50e3) + 0.5);
       if (const char* e = getenv("PBB_WAVE_C")) c = atoi(e);  // tuning override
       c = c < 1 ? 1 : (c > F ? F : c);
@@ -647,7 +648,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
         int dev = 0, sms = 0;
         PBB_CUDA(cudaGetDevice(&dev));
         PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        int cap = 2 * sms - kLoadReserve;
+        int cap = (int)(1.6 * (2 * sms - kLoadReserve));
         if (const char* e = getenv("PBB_ORDER_CAP")) cap = atoi(e);  // tuning override
         if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
       }

@@ -443,6 +443,92 @@ __device__ __forceinline__ void lean_chunk2(SMT& sm, int cb, int g, int st, int 
   }
 }
 
+// lean_chunk2 with the posterior computed ONCE per frame instead of once per slot group
+// (warp-specialised kernel only).  After the exchange of the partial quadratic forms, warp g
+// evaluates the softmax for frames 16g .. 16g+15 of the step's 64 (lanes 16-31 mirror lanes
+// 0-15), publishes gamma / q per (class, frame) and a second barrier hands it to all groups.
+// Saves (M - 1) / M of the softmax instructions and half of the partial-sum adds for one more
+// barrier per step.  sg then holds the sum of gamma over the frames THIS WARP evaluated; the
+// caller adds the groups' sums.
+template <int D, int K, typename CT, typename SMT>
+__device__ __forceinline__ void lean_chunk2_split(SMT& sm, int cb, int g, int st, int nsteps2, int lane, double eps,
+                                                  double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K]) {
+  using G = GroupDims<D>;
+  constexpr int NSG = G::NSG, NLOC = G::NLOC, M = G::M, NS = G::NS;
+  static_assert(M == 4, "frame split assumes four slot-group warps");
+  const CT* __restrict__ zrow = &sm.zbuf[st][2 * g][0] + lane;
+  const double* __restrict__ cg = &sm.coef[cb][0][g * NSG];
+  const int fsel = 16 * g + (lane & 15);         // frame of the step this lane evaluates
+  const int fhalf = fsel >> 5, fl = fsel & 31;   // its half (A / B) and lane
+#pragma unroll 1
+  for (int j = 0; j < nsteps2; ++j, zrow += 64) {
+    double psiA[NSG], psiB[NSG];
+    {
+      double2 x[NLOC];
+#pragma unroll
+      for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zrow + l * kStageFrames);
+      group_psi<D>(x, psiA);
+#pragma unroll
+      for (int l = 0; l < NLOC; ++l) x[l] = lds_cplx(zrow + l * kStageFrames + 32);
+      group_psi<D>(x, psiB);
+    }
+    double pA0[K], pA1[K], pB0[K], pB1[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { pA0[k] = 0.0; pA1[k] = 0.0; pB0[k] = 0.0; pB1[k] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NSG; i += 2) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const double2 cc = *reinterpret_cast<const double2*>(cg + k * NS + i);
+        pA0[k] = fma(cc.x, psiA[i], pA0[k]);
+        pB0[k] = fma(cc.x, psiB[i], pB0[k]);
+        pA1[k] = fma(cc.y, psiA[i + 1], pA1[k]);
+        pB1[k] = fma(cc.y, psiB[i + 1], pB1[k]);
+      }
+    }
+    double* __restrict__ xw = &sm.xq[0][g][0][lane];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      xw[k * 32] = pA0[k] + pA1[k];
+      xw[(K + k) * 32] = pB0[k] + pB1[k];
+    }
+    em_exchange_barrier<D, true>();
+    {
+      const double* __restrict__ xr = &sm.xq[0][0][fhalf * K][fl];
+      double q[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        double v = xr[k * 32];
+#pragma unroll
+        for (int gg = 1; gg < M; ++gg) v += xr[(gg * 2 * K + k) * 32];
+        q[k] = fabs(v);
+      }
+      double gm[K], cw[K];
+      softmax_product<D, K>(q, sm.ew[cb], eps, gm, cw);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        sg[k] += lane < 16 ? gm[k] : 0.0;
+        sm.cwx[k][fsel] = cw[k];
+      }
+    }
+    em_exchange_barrier<D, true>();
+    double cA[K], cB[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      cA[k] = sm.cwx[k][lane];
+      cB[k] = sm.cwx[k][32 + lane];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int i = 0; i < NSG; ++i) {
+        acc[k * NSG + i] = fma(cA[k], psiA[i], acc[k * NSG + i]);
+        acc[k * NSG + i] = fma(cB[k], psiB[i], acc[k * NSG + i]);
+      }
+    }
+  }
+}
+
 // General posterior (log domain or qmin-ratio form) with the reference's floors.
 template <int D, int K>
 __device__ __forceinline__ void softmax_general(const double (&q)[K], const double* __restrict__ ld,

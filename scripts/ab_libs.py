@@ -16,7 +16,8 @@ if sys.argv[1] == 'child':
         e0.record(); tr.fit(y, initialization=init, iterations=I); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ts.sort()
-    print('%-50s min %.3f  median %.3f ms' % (os.environ.get('PBB_LIB', 'default'), ts[0], ts[len(ts) // 2]), flush=True)
+    m = tr.fit(y, initialization=init, iterations=I)
+    print('%-50s min %.3f  median %.3f ms  checksum %.15e' % (os.environ.get('PBB_LIB', 'default'), ts[0], ts[len(ts) // 2], float(m.cacg.covariance_eigenvalues.sum())), flush=True)
 else:
     for lib in sys.argv[1:]:
         e = dict(os.environ)

@@ -23,7 +23,10 @@ if len(sys.argv) > 1 and sys.argv[1] == 'child':
     tr.fit(y_pin, initialization=init_pin, iterations=I); torch.cuda.synchronize()
     lib.pbb_profile_dump(); lib.pbb_profile_enable(0)
 else:
-    for env in ({}, {}, {}, {'PBB_ORDER_CAP': '276'}):
+    A = {'PBB_WAVE_C': '8', 'PBB_ORDER_CAP': '292'}
+    B = {'PBB_WAVE_C': '15', 'PBB_ORDER_CAP': '467'}
+    C = {'PBB_WAVE_C': '12', 'PBB_ORDER_CAP': '400'}
+    for env in (A, B, C, A, B, C, A, B, C):
         print('==', env, flush=True)
         e = dict(os.environ); e.update(env)
         subprocess.run(['timeout', '100', sys.executable, __file__, 'child'], env=e)
