@@ -1,5 +1,5 @@
 """Turn the raw gpurun_out/ artifacts of a measurement run into the committed summaries under profiles/.
-usage: python scripts/make_profiles.py <tag>   (expects gpurun_out/{bench_TAG.json, launches_TAG.csv, em_persistent_TAG.ncu-rep, ...})"""
+usage: python scripts/make_profiles.py <tag>   (expects gpurun_out/{bench_TAG.json, launches_TAG.csv, em_ws_TAG.ncu-rep, ...})"""
 import collections, csv, json, os, shutil, subprocess, sys
 tag = sys.argv[1]
 G, P = 'gpurun_out', 'profiles'
@@ -24,7 +24,7 @@ if os.path.exists(lc):
         f.write(f'{"kernel":70s} {"launches":>8s} {"total_us":>12s} {"share":>7s}\n')
         for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f'{k[:70]:70s} {n:8d} {t/1e3:12.1f} {100*t/tot:6.1f}%\n')
-rep = os.path.join(G, f'em_persistent_{tag}.ncu-rep')
+rep = os.path.join(G, f'em_ws_{tag}.ncu-rep')
 if os.path.exists(rep):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines())); h, u, v = rows[0], rows[1], rows[2]
@@ -43,15 +43,15 @@ if os.path.exists(rep):
             except ValueError: pass
     det = subprocess.run(['ncu', '-i', rep, '--page', 'details'], capture_output=True, text=True).stdout
     det = '\n'.join(l for l in det.splitlines() if l.strip() and not l.strip().startswith(('OPT', 'INF', 'Est.', '---')))
-    with open(os.path.join(P, f'em_persistent_{tag}_ncu_full.txt'), 'w') as f:
-        f.write('ncu --set full --clock-control none --import-source on -k regex:em_persistent -c 1 python scripts/one_fit.py 100\n')
+    with open(os.path.join(P, f'em_ws_{tag}_ncu_full.txt'), 'w') as f:
+        f.write('ncu --set full --clock-control none --import-source on -k regex:em_ws_kernel -c 1 python scripts/one_fit.py 100\n')
         f.write('one launch = 100 EM iterations of C2 (F=513 T=500 D=8 K=3, complex128); captured on NVIDIA B200 via gpurun\n')
         f.write('(numbers under ncu are NOT bench values)\n\n== selected raw metrics ==\n' + '\n'.join(lines) + '\n\n== details page ==\n' + det[:12000] + '\n')
     def by(k):
         val, unit = sel[k]
         mult = {'Mbyte': 1e6, 'Kbyte': 1e3, 'Gbyte': 1e9, 'byte': 1}.get(unit, 1)
         return val * mult
-    m = {'kernel': 'em_persistent_kernel<8,3,double2,false,2>', 'launch': '100 EM iterations, C2',
+    m = {'kernel': 'em_ws_kernel<3,double2>', 'launch': '100 EM iterations, C2',
          'dram_bytes_read': by('dram__bytes_read.sum'), 'dram_bytes_write': by('dram__bytes_write.sum'),
          'duration_ms_under_ncu': sel['gpu__time_duration.sum'][0],
          'fp64_pipe_active_pct': sel['sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed'][0],
@@ -60,5 +60,5 @@ if os.path.exists(rep):
     m['traffic_bytes_per_launch'] = m['dram_bytes_read'] + m['dram_bytes_write']
     json.dump(m, open(os.path.join(P, 'em_kernel_metrics.json'), 'w'), indent=1)
     bd = subprocess.run([sys.executable, 'scripts/ncu_breakdown.py', rep, '25'], capture_output=True, text=True).stdout
-    open(os.path.join(P, f'em_persistent_{tag}_source_breakdown.txt'), 'w').write(bd)
+    open(os.path.join(P, f'em_ws_{tag}_source_breakdown.txt'), 'w').write(bd)
     print(json.dumps(m))
