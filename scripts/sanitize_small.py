@@ -12,4 +12,11 @@ y6, _ = synth.structured_stft(7, 260, 6, 4, seed=2); i6 = synth.init_affiliation
 CWMMTrainer().fit(y6, initialization=i6, iterations=3)
 y3, _ = synth.structured_stft(3, 70, 3, 2, seed=3); i3 = synth.init_affiliation(3, 2, 70)
 CACGMMTrainer().fit(y3, initialization=i3, iterations=3)
+# streamed upload from pinned host memory (loader kernel + explicit task order) and K = 2 / 4 variants of the ws kernel
+import torch
+yp, ip = torch.from_numpy(y).pin_memory(), torch.from_numpy(init).pin_memory()
+CACGMMTrainer().fit(yp, initialization=ip, iterations=4)
+for K in (2, 4):
+    yk, _ = synth.structured_stft(9, 200, 8, K, seed=4); ik = synth.init_affiliation(9, K, 200)
+    CACGMMTrainer().fit(yk, initialization=ik, iterations=3)
 print('ok')

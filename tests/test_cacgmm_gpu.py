@@ -325,7 +325,8 @@ def test_inline_permutation_alignment_matches_reference_golden():
         CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=2, inline_permutation_aligner=al)
 
 
-@pytest.mark.parametrize('shape', [(129, 200, 4, 2, 20), (40, 333, 8, 3, 12), (7, 130, 6, 4, 5)])
+@pytest.mark.parametrize('shape', [(129, 200, 4, 2, 20), (40, 333, 8, 3, 12), (7, 130, 6, 4, 5), (3, 50, 8, 2, 3),
+                                   (65, 257, 8, 4, 1)])
 @pytest.mark.parametrize('cdtype', ['complex128', 'complex64'])
 def test_pinned_host_inputs_stream_in_and_match_device_inputs(shape, cdtype):
     """y / initialization in pinned host memory are read in place over PCIe by a loader kernel that
@@ -355,6 +356,34 @@ def test_pinned_host_inputs_stream_in_and_match_device_inputs(shape, cdtype):
     assert torch.equal(warm_pin.cacg.covariance_eigenvalues.cpu(), warm_dev.cacg.covariance_eigenvalues.cpu())
     # the model fitted from pinned memory predicts like any other
     np.testing.assert_array_equal(got.predict(y_pin.cuda()).cpu().numpy(), ref.predict(y_pin.cuda()).cpu().numpy())
+
+
+def test_warp_specialised_and_single_role_kernels_agree(tmp_path):
+    """D = 8 fits run on em_ws_kernel (producer / EM / update warps); PBB_NO_WS=1 selects the single-role
+    persistent kernel.  Same tasks, same arithmetic except the order in which sum(gamma) is accumulated."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import synth\n"
+        "from pb_bss_b200.distribution import CACGMMTrainer\n"
+        "out = {}\n"
+        "for (F, T, K, I) in ((21, 333, 3, 9), (10, 128, 2, 5), (6, 500, 4, 4)):\n"
+        "    y, _ = synth.structured_stft(F, T, 8, K, seed=3)\n"
+        "    m = CACGMMTrainer().fit(y, initialization=synth.init_affiliation(F, K, T, seed=7), iterations=I)\n"
+        "    out['w%%d' %% K] = m.weight; out['c%%d' %% K] = m.cacg.covariance\n"
+        "np.savez(sys.argv[1], **out)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = {}
+    for tag, env in (('ws', {}), ('single', {'PBB_NO_WS': '1'})):
+        path = str(tmp_path / f'{tag}.npz')
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, '-c', code, path], check=True, env=e, timeout=300)
+        res[tag] = np.load(path)
+    for k in res['ws'].files:
+        np.testing.assert_allclose(res['ws'][k], res['single'][k], rtol=1e-10, atol=1e-13)
 
 
 def test_argument_errors():
