@@ -95,6 +95,11 @@ typedef struct pbb_cacgmm_options {
                               bit 1: no streamed upload (see pbb_cacgmm_fit) */
 } pbb_cacgmm_options;
 
+/* Host-only helper (no GPU needed): the task order pbb_cacgmm_fit uses for a streamed upload.
+ * order (HOST, F * iterations ints): order[ticket] = bin | iteration << 16.  `arrive` bins join
+ * per time slot, at most `cap` tasks run per slot; every (bin, it) comes after (bin, it - 1). */
+int pbb_streamed_task_order(int F, int iterations, int arrive, int cap, int* order);
+
 /* Bytes of scratch pbb_cacgmm_fit / _predict need for this problem size. */
 size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K);
 

@@ -257,20 +257,10 @@ constexpr int kLoadCtas = 16;    // stream_load_kernel grid
 // A task still only depends on a lower ticket ((b, it - 1) sits in an earlier slot).
 // The table (4 bytes per task) is built once per (device, F, iterations, arrive, cap) and kept in a
 // small library-owned device cache -- the only device memory the library allocates itself.
-static int streamed_order(int F, int I, int arrive, int cap, const int** out) {
-  static std::mutex mu;
-  static std::map<std::array<int, 5>, int*> cache;
-  std::lock_guard<std::mutex> lk(mu);
-  int dev = 0;
-  PBB_CUDA(cudaGetDevice(&dev));
-  const std::array<int, 5> key{dev, F, I, arrive, cap};
-  auto hit = cache.find(key);
-  if (hit != cache.end()) { *out = hit->second; return 0; }
-  if (cache.size() >= 16) {
-    for (auto& kv : cache) cudaFree(kv.second);
-    cache.clear();
-  }
-  std::vector<int> order;
+// host part of streamed_order: order[ticket] = bin | iteration << 16 (also exported for the CPU tests
+// as pbb_streamed_task_order)
+static void build_streamed_order(int F, int I, int arrive, int cap, std::vector<int>& order) {
+  order.clear();
   order.reserve((size_t)F * I);
   std::vector<int> done(F, 0), count(I + 1), pick;
   for (long long slot = 0; order.size() < (size_t)F * I; ++slot) {
@@ -293,6 +283,23 @@ static int streamed_order(int F, int I, int arrive, int cap, const int** out) {
       ++done[*p];
     }
   }
+}
+
+static int streamed_order(int F, int I, int arrive, int cap, const int** out) {
+  static std::mutex mu;
+  static std::map<std::array<int, 5>, int*> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  const std::array<int, 5> key{dev, F, I, arrive, cap};
+  auto hit = cache.find(key);
+  if (hit != cache.end()) { *out = hit->second; return 0; }
+  if (cache.size() >= 16) {
+    for (auto& kv : cache) cudaFree(kv.second);
+    cache.clear();
+  }
+  std::vector<int> order;
+  build_streamed_order(F, I, arrive, cap, order);
   int* d = nullptr;
   PBB_CUDA(cudaMalloc(&d, order.size() * sizeof(int)));
   PBB_CUDA(cudaMemcpy(d, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -502,6 +509,18 @@ int pbb_normalize_observation(const void* y, void* z, int F, int T, int D, int d
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == PBB_C128 ? launch_normalize<double2>(y, z, F, T, D, swap, T, st)
                            : launch_normalize<float2>(y, z, F, T, D, swap, T, st);
+}
+
+int pbb_streamed_task_order(int F, int iterations, int arrive, int cap, int* order) {
+  PBB_CHECK_ARG(F > 0 && F <= 65535, 1, "need 0 < F < 65536");
+  PBB_CHECK_ARG(iterations > 0 && iterations < 32768, 2, "need 0 < iterations < 32768");
+  PBB_CHECK_ARG(arrive > 0, 3, "arrive must be positive");
+  PBB_CHECK_ARG(cap > 0, 4, "cap must be positive");
+  PBB_CHECK_ARG(order != nullptr, 5, "order is null");
+  std::vector<int> o;
+  build_streamed_order(F, iterations, arrive, cap, o);
+  memcpy(order, o.data(), o.size() * sizeof(int));
+  return 0;
 }
 
 size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K) {

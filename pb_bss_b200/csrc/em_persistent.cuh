@@ -708,6 +708,8 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
                                                   const int* __restrict__ tab, double* __restrict__ ld_out) {
   constexpr int NS = D * D;
   double* Ad = reinterpret_cast<double*>(A);
+    // L2 round trip issued first, consumed after the inversion
+    const int dead_bin = a.dead == nullptr ? 0 : __ldcg(a.dead + bin);
     const double scale = (double)D / fmax(Sk[NS], kTiny);
     bool bad = false;
     auto build = [&]() {
@@ -743,7 +745,7 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
     // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
     // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
     const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
-                          (a.dead == nullptr || __ldcg(a.dead + bin) == 0);
+                          dead_bin == 0;
     double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
     if (__any_sync(0xffffffffu, bad)) {
       if (lane == 0) atomicMax(a.status, bin + 1);

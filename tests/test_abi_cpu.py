@@ -82,3 +82,24 @@ def test_weight_axis_mapping():
         _weight_mode((-3,), 4)  # more than one independent dim
     with pytest.raises(NotImplementedError):
         _weight_mode((-4, -1), 4)
+
+
+@pytest.mark.parametrize('F,I,arrive,cap', [(513, 100, 15, 467), (129, 20, 30, 292), (7, 5, 1, 292), (40, 12, 3, 10),
+                                            (513, 1, 8, 292), (1, 9, 4, 4), (2000, 3, 64, 50)])
+def test_streamed_task_order_is_a_valid_schedule(F, I, arrive, cap):
+    """Host logic of the streamed upload (api_cacgmm.cu, build_streamed_order): every (bin, iteration) exactly
+    once, (bin, it) after (bin, it - 1), bins entering in ascending (= arrival) order -- the properties the
+    persistent kernel's no-deadlock argument rests on."""
+    from pb_bss_b200 import _lib
+    lib = _lib.load()
+    order = np.zeros(F * I, dtype=np.int32)
+    rc = lib.pbb_streamed_task_order(F, I, arrive, cap, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert rc == 0
+    bins, its = order & 0xffff, order >> 16
+    assert bins.min() >= 0 and bins.max() == F - 1 and its.min() == 0 and its.max() == I - 1
+    assert len(set(zip(bins.tolist(), its.tolist()))) == F * I
+    pos = np.empty((F, I), dtype=np.int64)
+    pos[bins, its] = np.arange(F * I)
+    assert (np.diff(pos, axis=1) > 0).all()
+    assert (np.diff(pos[:, 0]) > 0).all()               # bins enter in the order in which they arrive
+    assert lib.pbb_streamed_task_order(F, 0, arrive, cap, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == -2
