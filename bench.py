@@ -234,6 +234,11 @@ def b200_arm(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # the end-to-end path must produce the resident path's model (checked outside the timed regions)
+    m_res = step_resident()
+    out_e2e = step_e2e()
+    e2e_identical = bool(torch.equal(out_e2e[2], m_res.cacg.covariance_eigenvalues.cpu())
+                         and torch.equal(out_e2e[1], m_res.cacg.covariance_eigenvectors.cpu()))
     # dominant-kernel timing: an extra, event-instrumented fit right after the timed region
     prof = None
     if rank == 0:
@@ -300,6 +305,7 @@ def b200_arm(args):
                 'h2d_bytes_per_step': int(y_host.nbytes + init_host.nbytes),
                 'd2h_bytes_per_step': int(F * K * (D * D * 16 + D * 8 + 8)),
                 'frames_bins_per_s': e2e * F * T,
+                'model_identical_to_resident_path': e2e_identical,
                 'transfer': 'CACGMMTrainer.fit on pinned host tensors: observation + initial affiliations are '
                             'read over PCIe by a loader kernel that overlaps the EM kernel, the model is '
                             'written to pinned host memory by the final update kernel; timed with the host '
