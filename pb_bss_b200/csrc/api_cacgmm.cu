@@ -683,9 +683,12 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     }
 #ifdef PBB_PHASE_TIMING
     {
-      unsigned long long ph[8];
+      unsigned long long ph[12];
       cudaStreamSynchronize(st);
       cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[phase] update of class 0, cycles per task: build %.0f  gauss-jordan %.0f  logdet/tinv %.0f  stores %.0f\n",
+              ph[8] / (double)((size_t)F * opt->iterations), ph[9] / (double)((size_t)F * opt->iterations),
+              ph[10] / (double)((size_t)F * opt->iterations), ph[11] / (double)((size_t)F * opt->iterations));
       unsigned long long tot = 0;
       for (int i = 0; i < 8; ++i) tot += ph[i];
       static const char* nm[8] = {"ticket+flag / model wait", "chunk-top / updater busy", "tma-wait", "em-steps", "reduce", "update / S wait", "publish / hand-over", "task-start / updater idle"};

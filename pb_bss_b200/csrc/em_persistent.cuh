@@ -710,6 +710,12 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
   double* Ad = reinterpret_cast<double*>(A);
     // L2 round trip issued first, consumed after the inversion
     const int dead_bin = a.dead == nullptr ? 0 : __ldcg(a.dead + bin);
+#ifdef PBB_PHASE_TIMING
+    long long _tu = clock64();
+#define PBB_PHU(i) do { if (k == 0 && lane == 0) { long long _t = clock64(); atomicAdd(&a.phase[i], (unsigned long long)(_t - _tu)); _tu = _t; } } while (0)
+#else
+#define PBB_PHU(i) do { } while (0)
+#endif
     const double scale = (double)D / fmax(Sk[NS], kTiny);
     bool bad = false;
     auto build = [&]() {
@@ -734,8 +740,10 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
     const double tn = a.covariance_norm == PBB_NORM_NONE ? 1.0 : (double)D / fmax(tr, kTiny);
     for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
     __syncwarp();
+    PBB_PHU(8);   // build + trace + scale
     bool ok;
     const double det = warp_hpd_inverse<D>(A, lane, &ok);
+    PBB_PHU(9);   // Gauss-Jordan
     double ldk = log(det);
     double tinv = 0.0;
     for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
@@ -747,6 +755,7 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
     const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
                           dead_bin == 0;
     double* __restrict__ co = a.coef + ((size_t)bin * K + k) * NS;
+    PBB_PHU(10);  // log det, trace of the inverse, floor test
     if (__any_sync(0xffffffffu, bad)) {
       if (lane == 0) atomicMax(a.status, bin + 1);
     }
@@ -786,6 +795,7 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
         a.ew[(size_t)bin * 4 + k] = Sk[NS];
       }
     }
+    PBB_PHU(11);  // coefficient stores
 }
 
 template <int D, int K, typename CT, bool FULL, int FPL, int MODEL = 0>
