@@ -696,6 +696,7 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     }
 #endif
     u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model
+    u.coef = nullptr;  // nobody reads the E-step form of the final model
     return launch_update(u, st);
   }
   int it = 0;

@@ -570,9 +570,11 @@ __global__ void cacg_update_kernel(const UpdArgs u) {
       lo[r] = lam[x];
       for (int d = 0; d < D; ++d) Vo[d * D + r] = V[d * D + x];
     }
-    // 6. E-step form of the model
-    const double ldk = model_from_eig_warp(V, lam, tab, D, lane, u.coef + ((size_t)f * K + k) * NS);
-    if (lane == 0) ld_s[k] = ldk;
+    // 6. E-step form of the model (not needed after the last iteration of a fit: coef == nullptr)
+    if (u.coef != nullptr) {
+      const double ldk = model_from_eig_warp(V, lam, tab, D, lane, u.coef + ((size_t)f * K + k) * NS);
+      if (lane == 0) ld_s[k] = ldk;
+    }
     __syncwarp();
   }
   __syncthreads();
@@ -588,11 +590,13 @@ __global__ void cacg_update_kernel(const UpdArgs u) {
       for (int j = 0; j < K; ++j) n1 += fabs(sumg[j]);
       wk = sumg[k] / (n1 == 0.0 ? 1e-10 : n1);
     }
-    double ldmin = ld_s[0];
-    for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, ld_s[j]);
     u.weight[(size_t)f * K + k] = wk;
-    u.ld[(size_t)f * K + k] = ld_s[k];
-    u.ew[(size_t)f * K + k] = wk * exp(ldmin - ld_s[k]);
+    if (u.coef != nullptr) {
+      double ldmin = ld_s[0];
+      for (int j = 1; j < K; ++j) ldmin = fmin(ldmin, ld_s[j]);
+      u.ld[(size_t)f * K + k] = ld_s[k];
+      u.ew[(size_t)f * K + k] = wk * exp(ldmin - ld_s[k]);
+    }
   }
 }
 
