@@ -718,11 +718,11 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
 #endif
     const double scale = (double)D / fmax(Sk[NS], kTiny);
     bool bad = false;
-    auto build = [&]() {
+    auto build_scaled = [&](double f) {
       for (int s = lane; s < NS; s += 32) {
         const int pk = tab[s];
         const int d = pk & 255, e = (pk >> 8) & 255, kind = pk >> 16;
-        const double v = Sk[s] * scale;
+        const double v = Sk[s] * f;
         bad |= !isfinite(v);
         if (kind == 0) { Ad[2 * (d * D + d)] = v; Ad[2 * (d * D + d) + 1] = 0.0; }
         else if (kind == 1) { Ad[2 * (d * D + e)] = v; Ad[2 * (e * D + d)] = v; }
@@ -730,24 +730,34 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
       }
       __syncwarp();
     };
-    build();
-    // trace-normalise to tr = D: keeps all classes on a comparable scale
-    double tr = 0.0;
-    for (int d = lane; d < D; d += 32) tr += A[d * D + d].x;
-    tr = warp_sum(tr);
+    auto build = [&]() { build_scaled(scale); };
+    // Trace-normalise to tr = D (keeps all classes on a comparable scale): the factor D / tr(S) is applied
+    // while the matrix is built (the 1 / sum(gamma) scale cancels), the diagonal slots are read directly.
     // covariance_norm=False keeps the reference's absolute scale (it survives into the returned
-    // eigenvalues); otherwise the scale is free and tr = D keeps all classes comparable
-    const double tn = a.covariance_norm == PBB_NORM_NONE ? 1.0 : (double)D / fmax(tr, kTiny);
-    for (int i = lane; i < NS; i += 32) { A[i].x *= tn; A[i].y *= tn; }
-    __syncwarp();
+    // eigenvalues).
+    double tr, tn;
+    if (a.covariance_norm == PBB_NORM_NONE) {
+      build();
+      tr = 0.0;
+      for (int d = lane; d < D; d += 32) tr += A[d * D + d].x;
+      tr = warp_sum(tr);
+      tn = 1.0;
+    } else {
+      double trs = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) trs += Sk[(d >> 1) * (NS / (D / 2)) + (d & 1)];  // |z_d|^2 slots (common.cuh)
+      tr = trs * scale;
+      tn = (double)D / fmax(tr, kTiny);
+      build_scaled(scale * tn);
+    }
     PBB_PHU(8);   // build + trace + scale
     bool ok;
     const double det = warp_hpd_inverse<D>(A, lane, &ok);
     PBB_PHU(9);   // Gauss-Jordan
     double ldk = log(det);
     double tinv = 0.0;
-    for (int d = lane; d < D; d += 32) tinv += A[d * D + d].x;
-    tinv = warp_sum(tinv);
+#pragma unroll
+    for (int d = 0; d < D; ++d) tinv += A[d * D + d].x;  // every lane reads the diagonal (broadcast loads)
     // lambda_min / lambda_max >= 1 / (tr(A) tr(A^-1))
     // A bin with an all-zero frame must keep the reference's own normalisation: such a frame has
     // q = `tiny` for every class whatever the scale of B (cacg.py:198), so its posterior depends
