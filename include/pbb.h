@@ -156,10 +156,12 @@ int pbb_cacgmm_mstep(const void* y, int dtype, int F, int T, int D, int K,
                      void* stream);
 
 /* estimate_mixture_weight with weight_constant_axis=(-3,) / (-3, -1)
- * (mixture_model_utils.py:133-203, no saliency): weight_kt[k][t] = mean over bins of
- * affiliation[f][k][t]; with also_over_time additionally weight_k[k] = mean over t. */
+ * (mixture_model_utils.py:133-203): weight_kt[k][t] = mean over bins of
+ * affiliation[f][k][t]; flags bit 0: additionally weight_k[k] = mean over t; flags bit 1:
+ * the saliency form (:192-203, what CWMMTrainer uses, cwmm.py:129-130): the result is
+ * L1-normalised over the classes (zero norm -> 1e-10). */
 int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T,
-                                 int also_over_time, double* weight_kt,
+                                 int flags, double* weight_kt,
                                  double* weight_k, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -184,10 +186,12 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K,
                  double* weight, void* workspace, size_t workspace_bytes,
                  int* status, void* stream);
 
-/* CWMM.predict (cwmm.py:26-52): affiliation (F, K, T) out. weight may be NULL (1/K). */
+/* CWMM.predict (cwmm.py:26-52): affiliation (F, K, T) out.  weight: (F, K) for
+ * PBB_WEIGHT_TIME, ignored (1/K) for PBB_WEIGHT_CONST, (K, T) / (K) for the
+ * frequency-tied PBB_WEIGHT_TIED_TIME / PBB_WEIGHT_TIED (weight_constant_axis (-3,) / (-3, -1)). */
 int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K,
                      const void* mode, const double* concentration,
-                     const double* weight, double* affiliation,
+                     const double* weight, int weight_mode, double* affiliation,
                      void* workspace, size_t workspace_bytes, int* status,
                      void* stream);
 

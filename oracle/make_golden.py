@@ -155,6 +155,27 @@ def make_cwmm(ref):
                 np.linspace(0, 500, 101), D))
 
 
+def make_cwmm_coupled(ref):
+    """CWMMTrainer with frequency-tied weights and the inline permutation alignment (cwmm.py:76-240)."""
+    T = ref.distribution.CWMMTrainer
+    pa = ref.permutation_alignment
+    y = synth.structured_stft(65, 60, 4, 2, seed=21)[0]
+    F, N, D = y.shape
+    K = 2
+    init = synth.init_affiliation(F, K, N, seed=13)
+    for name, axis, inline in (('cwmm_tied_time', (-3,), False), ('cwmm_tied', (-3, -1), False),
+                               ('cwmm_inline_pa', (-3,), True)):
+        al = pa.DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+                                         main_iterations=5, sub_iterations=2) if inline else None
+        model = T().fit(y, initialization=init, iterations=4, weight_constant_axis=axis,
+                        inline_permutation_aligner=al)
+        out = dict(y=y, init=init, iterations=4, weight=model.weight, mode=model.complex_watson.mode,
+                   concentration=model.complex_watson.concentration, affiliation=model.predict(y))
+        if inline:
+            out['plan'] = np.asarray(al.alignment_plan)
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+
+
 def make_permutation(ref):
     pa = ref.permutation_alignment
     rng = np.random.RandomState(31)
@@ -272,6 +293,7 @@ def main():
     make_cacgmm_coupled(ref)
     make_cacg_steps(ref)
     make_cwmm(ref)
+    make_cwmm_coupled(ref)
     make_permutation(ref)
     make_permutation_greedy_oracle(ref)
     make_beamformer(ref)

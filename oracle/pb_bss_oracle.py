@@ -317,9 +317,11 @@ def cwmm_predict(y, model):
 
 def cwmm_fit(y, initialization, iterations=100, *, saliency=None,
              weight_constant_axis=(-1,), max_concentration=500,
-             spline_markers=1000):
+             spline_markers=1000, inline_permutation_plan=None):
     """EM loop of ``CWMMTrainer.fit`` (pb_bss/distribution/cwmm.py:76-240).
 
+    ``inline_permutation_plan``: alignment plan of a DHTVPermutationAlignment run after every
+    E-step (``inline_permutation_aligner``, cwmm.py:169-174, mixture_model_utils.py:264-306).
     Returns dict(weight, mode, concentration).
     """
     assert np.iscomplexobj(y), y.dtype
@@ -334,6 +336,10 @@ def cwmm_fit(y, initialization, iterations=100, *, saliency=None,
         if model is not None:
             # CWMM.predict re-normalises y every iteration (cwmm.py:35-37,166)
             affiliation = cwmm_predict(z, model)
+            if inline_permutation_plan is not None:
+                mask = np.ascontiguousarray(np.transpose(affiliation, (1, 0, 2)))
+                mapping = dhtv_calculate_mapping(mask, inline_permutation_plan)
+                affiliation = np.transpose(apply_mapping(mask, mapping), (1, 0, 2))
         weight = estimate_mixture_weight(affiliation, saliency,
                                          weight_constant_axis)
         masked = affiliation * saliency[..., None, :]

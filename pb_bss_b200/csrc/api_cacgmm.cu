@@ -70,6 +70,16 @@ __global__ void mean_over_time_kernel(const double* __restrict__ in, int K, int 
   }
 }
 
+// w[k][t] /= sum_k |w[k][t]|  (a zero norm counts as 1e-10)
+__global__ void unit_norm_over_classes_kernel(double* __restrict__ w, int K, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double n = 0.0;
+  for (int k = 0; k < K; ++k) n += fabs(w[(size_t)k * T + t]);
+  if (n == 0.0) n = 1e-10;
+  for (int k = 0; k < K; ++k) w[(size_t)k * T + t] /= n;
+}
+
 // ---- workspace carving -------------------------------------------------------
 struct CacgmmWorkspace {
   void* z;
@@ -898,15 +908,17 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
 }
 
 int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K, const void* mode,
-                     const double* concentration, const double* weight, double* affiliation, void* workspace,
-                     size_t workspace_bytes, int* status, void* stream) {
+                     const double* concentration, const double* weight, int weight_mode, double* affiliation,
+                     void* workspace, size_t workspace_bytes, int* status, void* stream) {
   PBB_CHECK_ARG(y != nullptr, 1, "y is null");
   if (int r = check_shape(F, T, D, K, dtype)) return r;
   PBB_CHECK_ARG(mode && concentration, 7, "model is null");
-  PBB_CHECK_ARG(affiliation != nullptr, 10, "affiliation output is null");
-  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 11,
+  PBB_CHECK_ARG(weight_mode >= 0 && weight_mode <= PBB_WEIGHT_TIED, 10, "bad weight_mode");
+  PBB_CHECK_ARG(weight != nullptr || weight_mode == PBB_WEIGHT_CONST, 9, "weight is null");
+  PBB_CHECK_ARG(affiliation != nullptr, 11, "affiliation output is null");
+  PBB_CHECK_ARG(workspace != nullptr && workspace_bytes >= pbb_cacgmm_workspace_bytes(F, T, D, K), 12,
                 "workspace too small (pbb_cwmm_workspace_bytes)");
-  PBB_CHECK_ARG(status != nullptr, 13, "status is null");
+  PBB_CHECK_ARG(status != nullptr, 14, "status is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CacgmmWorkspace ws = carve(workspace, F, T, D, K);
   PBB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
@@ -915,7 +927,9 @@ int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K, const
   if (r) return r;
   CwFromModelArgs fm;
   fm.F = F; fm.D = D; fm.K = K;
-  fm.mode = reinterpret_cast<const double2*>(mode); fm.concentration = concentration; fm.weight = weight;
+  const bool tied = weight_mode == PBB_WEIGHT_TIED_TIME || weight_mode == PBB_WEIGHT_TIED;
+  fm.mode = reinterpret_cast<const double2*>(mode); fm.concentration = concentration;
+  fm.weight = (tied || weight_mode == PBB_WEIGHT_CONST) ? nullptr : weight;
   fm.coef = ws.coef; fm.ld = ws.ld; fm.ew = ws.ew; fm.w = ws.w;
   {
     LaunchScope ls("cw_from_model_kernel", st);
@@ -927,21 +941,29 @@ int pbb_cwmm_predict(const void* y, int dtype, int F, int T, int D, int K, const
   a.z = ws.z; a.zs = ws.zs; a.F = F; a.T = T; a.D = D; a.K = K;
   a.mode = kModeE; a.model_kind = 1;
   a.coef = ws.coef; a.ld = ws.ld; a.w = ws.w; a.ew = ws.ew;
+  if (tied) { a.w_time = weight; a.w_time_st = weight_mode == PBB_WEIGHT_TIED_TIME ? 1 : 0; }
   a.aff_out = affiliation;
   int nch = launch_em(a, dtype, 0, st);
   return nch > 0 ? 0 : (nch ? nch : 1);
 }
 
-int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T, int also_over_time, double* weight_kt,
+int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T, int flags, double* weight_kt,
                                  double* weight_k, void* stream) {
+  const int also_over_time = flags & 1, unit_norm = flags & 2;
   PBB_CHECK_ARG(affiliation != nullptr, 1, "affiliation is null");
-  PBB_CHECK_ARG(F > 0 && K > 0 && T > 0, 2, "bad shape");
+  PBB_CHECK_ARG(F > 0 && K > 0 && K < kMaxK && T > 0, 2, "bad shape");
   PBB_CHECK_ARG(weight_kt != nullptr, 6, "weight (K, T) output is null");
   PBB_CHECK_ARG(!also_over_time || weight_k != nullptr, 7, "weight (K) output is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   LaunchScope ls("mean_over_bins_kernel", st);
   mean_over_bins_kernel<<<(K * T + 255) / 256, 256, 0, st>>>(affiliation, F, K, T, weight_kt);
   if (also_over_time) mean_over_time_kernel<<<K, 256, 0, st>>>(weight_kt, K, T, weight_k);
+  if (unit_norm) {
+    // the saliency form of estimate_mixture_weight (mixture_model_utils.py:192-203, used by CWMMTrainer):
+    // sums instead of means, then _unit_norm(ord=1, axis=-2, eps=1e-10, 'where') -- the 1/F (1/T) cancels
+    if (also_over_time) unit_norm_over_classes_kernel<<<1, 32, 0, st>>>(weight_k, K, 1);
+    else unit_norm_over_classes_kernel<<<(T + 127) / 128, 128, 0, st>>>(weight_kt, K, T);
+  }
   PBB_CUDA(cudaGetLastError());
   return 0;
 }

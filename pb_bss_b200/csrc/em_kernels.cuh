@@ -207,7 +207,14 @@ __device__ __forceinline__ void em_fast_group(const EmArgs& a, EmFastSmem<D, K>&
       double ll;
       const uint8_t* act = a.activity ? a.activity + ((size_t)f * K) * T + (valid ? t : 0) : nullptr;
       if (a.model_kind == 1) {
-        watson_softmax<K>(q, sm.ld, sm.w, sm.ew, gam);
+        if (a.w_time != nullptr) {  // frequency-tied weights, see below
+          double wl[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) wl[k] = a.w_time[(size_t)k * (a.w_time_st ? T : 1) + (a.w_time_st && valid ? t : 0)];
+          watson_softmax<K>(q, sm.ld, wl, sm.ew, gam);
+        } else {
+          watson_softmax<K>(q, sm.ld, sm.w, sm.ew, gam);
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) invq[k] = 1.0;
         ll = 0.0;

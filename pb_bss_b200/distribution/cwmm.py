@@ -34,8 +34,14 @@ class CWMM(_ProbabilisticModel):
         kappa = _device.to_device(self.complex_watson.concentration, torch.float64)
         kappa = kappa.expand(*independent, K).reshape(F, K).contiguous()
         w = _device.to_device(self.weight, torch.float64)
-        assert w.shape[-1] == 1, w.shape
-        w = w[..., 0].expand(*independent, K).reshape(F, K).contiguous()
+        wmode = _lib.WEIGHT_TIME
+        if w.shape[-1] != 1:
+            # frequency-tied weights (weight_constant_axis=(-3,), mixture_model_utils.py:187-190): (1, K, N)
+            assert w.shape[-1] == N and all(int(n) == 1 for n in w.shape[:-2]), (w.shape, N)
+            w = w.reshape(K, N).contiguous()
+            wmode = _lib.WEIGHT_TIED_TIME
+        else:
+            w = w[..., 0].expand(*independent, K).reshape(F, K).contiguous()
         aff = _device.empty((F, K, N), torch.float64)
         status = _device.empty((1,), torch.int32)
         lib = _lib.load()
@@ -43,7 +49,7 @@ class CWMM(_ProbabilisticModel):
         ws = _device.workspace(nbytes)
         _lib.check(lib.pbb_cwmm_predict(
             _device.ptr(yd), code, F, N, D, K, _device.ptr(mode),
-            _device.ptr(kappa), _device.ptr(w), _device.ptr(aff),
+            _device.ptr(kappa), _device.ptr(w), wmode, _device.ptr(aff),
             _device.ptr(ws), nbytes, _device.ptr(status),
             _device.stream_ptr()), 'pbb_cwmm_predict')
         _status_check(status, 'CWMM.predict')
@@ -76,10 +82,6 @@ class CWMMTrainer:
             'Exactly one of the two inputs has to be None: '
             f'{initialization is None} xor {num_classes is None}')
         assert affiliation_eps == 0, affiliation_eps  # cwmm.py:161
-        if inline_permutation_aligner is not None:
-            raise NotImplementedError(
-                'inline_permutation_aligner is not on the device yet '
-                '(SURVEY.md section 8f, rank 2)')
         like_numpy = not _device.is_tensor(y)
         yd = _device.to_device(y)
         assert yd.is_complex(), yd.dtype
@@ -106,6 +108,17 @@ class CWMMTrainer:
                 'you are using to fit a model. Use a new trainer, when you '
                 'change the dimension.')
         weight_mode = _weight_mode(weight_constant_axis, len(independent) + 2)
+        tied = weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED)
+        if inline_permutation_aligner is not None or tied:
+            return self._fit_coupled(yd, like_numpy, init, sal, K, iterations, weight_mode,
+                                     inline_permutation_aligner, weight_constant_axis)
+        return self._fit_device(yd, like_numpy, init, sal, K, iterations, weight_mode)
+
+    def _fit_device(self, yd, like_numpy, init, sal, K, iterations, weight_mode):
+        """All iterations in one C-ABI call (bins independent).  With ``iterations=1`` this is exactly the
+        reference's ``_m_step`` from the given affiliations (cwmm.py:220-240)."""
+        code = _device.complex_dtype_code(yd)
+        independent, F, N, D = _flatten_obs(yd)
         t_dev, c_dev = self.complex_watson_trainer.device_spline_table()
         mode = _device.empty((F, K, D), torch.complex128)
         kappa = _device.empty((F, K), torch.float64)
@@ -133,6 +146,49 @@ class CWMMTrainer:
             complex_watson=ComplexWatson(
                 mode=_device.to_host(mode.reshape(*independent, K, D), like_numpy),
                 concentration=_device.to_host(kappa.reshape(*independent, K), like_numpy)))
+
+    def _fit_coupled(self, yd, like_numpy, init, sal, K, iterations, weight_mode, aligner, weight_constant_axis):
+        """EM with per-iteration coupling across bins (cwmm.py:152-184): frequency-tied weights
+        (``weight_constant_axis`` (-3,) / (-3, -1)) and / or the inline permutation alignment
+        (mixture_model_utils.py:264-306).  Every step runs on the device."""
+        from ..permutation_alignment import apply_mapping
+        independent, F, N, D = _flatten_obs(yd)
+        tied = weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED)
+        if aligner is not None:
+            message = ('Inline permutation alignment reduces mismatch between frequency independent '
+                       'mixtures weights and a frequency independent observation model. Therefore, we '
+                       f'require `affiliation.ndim == 3` and a corresponding `weight_constant_axis` '
+                       f'({weight_constant_axis}).')
+            assert len(independent) == 1 and tied, message
+        if tied and sal is not None:
+            raise NotImplementedError('saliency together with frequency-tied weights is not on the device yet')
+        lib = _lib.load()
+        affiliation = init
+        model = None
+        for _ in range(iterations):
+            if model is not None:
+                affiliation = model.predict(yd).reshape(F, K, N)
+                if aligner is not None:
+                    mask_kft = affiliation.permute(1, 0, 2).contiguous()
+                    mapping = aligner.calculate_mapping(mask_kft)
+                    affiliation = apply_mapping(mask_kft, mapping).permute(1, 0, 2).contiguous()
+            # mode / concentration of every (bin, class) from the affiliations; per-bin weights unless tied
+            model = self._fit_device(yd, False, affiliation.contiguous(), sal, K, 1,
+                                     _lib.WEIGHT_TIME if tied else weight_mode)
+            if tied:
+                w_kt = _device.empty((K, N), torch.float64)
+                w_k = _device.empty((K,), torch.float64)
+                flags = (1 if weight_mode == _lib.WEIGHT_TIED else 0) | 2
+                _lib.check(lib.pbb_mixture_weight_over_bins(
+                    _device.ptr(affiliation.contiguous()), F, K, N, flags, _device.ptr(w_kt), _device.ptr(w_k),
+                    _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
+                model.weight = w_kt[None] if weight_mode == _lib.WEIGHT_TIED_TIME else w_k[None, :, None]
+        if like_numpy:
+            model = CWMM(
+                weight=_device.to_host(model.weight, True) if _device.is_tensor(model.weight) else model.weight,
+                complex_watson=ComplexWatson(mode=_device.to_host(model.complex_watson.mode, True),
+                                             concentration=_device.to_host(model.complex_watson.concentration, True)))
+        return model
 
     def fit_predict(self, y, initialization=None, num_classes=None,
                     iterations=100, **kwargs):

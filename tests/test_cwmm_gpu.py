@@ -25,6 +25,30 @@ def test_fit_matches_reference_golden(name):
     np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize('name,axis', [('cwmm_tied_time', (-3,)), ('cwmm_tied', (-3, -1)), ('cwmm_inline_pa', (-3,))])
+def test_coupled_fit_matches_reference_golden(name, axis):
+    """Frequency-tied weights (weight_constant_axis (-3,) / (-3, -1)) and the inline permutation alignment
+    (cwmm.py:152-184): per-iteration loop of device kernels, fixtures from the unmodified reference."""
+    from pb_bss_b200.distribution import CWMMTrainer
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+    g = load_golden(name)
+    al = None
+    if 'plan' in g:
+        al = DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
+                                      main_iterations=5, sub_iterations=2)
+        assert al.alignment_plan == g['plan'].tolist()
+    model = CWMMTrainer().fit(g['y'], initialization=g['init'], iterations=int(g['iterations']),
+                              weight_constant_axis=axis, inline_permutation_aligner=al)
+    assert model.weight.shape == g['weight'].shape
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.complex_watson.concentration, g['concentration'], rtol=1e-6)
+    np.testing.assert_allclose(cos_similarity(model.complex_watson.mode, g['mode']), 1, atol=1e-9)
+    np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-5, atol=1e-8)
+    if al is not None:
+        with pytest.raises(AssertionError):  # needs frequency-tied weights, like the reference
+            CWMMTrainer().fit(g['y'], initialization=g['init'], iterations=2, inline_permutation_aligner=al)
+
+
 @pytest.mark.parametrize('F,T,D,K,I', [(9, 150, 6, 4, 6), (5, 64, 8, 3, 5), (4, 100, 3, 2, 5), (3, 90, 5, 3, 4)])
 def test_fit_matches_oracle(F, T, D, K, I):
     from pb_bss_b200.distribution import CWMMTrainer

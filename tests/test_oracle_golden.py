@@ -144,6 +144,20 @@ def test_cwmm_fit_matches_reference(name):
                                rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize('name,axis', [('cwmm_tied_time', (-3,)), ('cwmm_tied', (-3, -1)), ('cwmm_inline_pa', (-3,))])
+def test_cwmm_coupled_fit_matches_reference(name, axis):
+    # frequency-tied weights / inline permutation alignment, cwmm.py:152-184
+    g = load_golden(name)
+    plan = g['plan'].tolist() if 'plan' in g else None
+    model = O.cwmm_fit(g['y'], g['init'], int(g['iterations']), weight_constant_axis=axis,
+                       inline_permutation_plan=plan)
+    assert model['weight'].shape == g['weight'].shape
+    np.testing.assert_allclose(model['weight'], g['weight'], rtol=1e-9)
+    np.testing.assert_allclose(model['concentration'], g['concentration'], rtol=1e-7)
+    np.testing.assert_allclose(cos_similarity(model['mode'], g['mode']), 1, atol=1e-9)
+    np.testing.assert_allclose(O.cwmm_predict(g['y'], model), g['affiliation'], rtol=1e-6, atol=1e-9)
+
+
 @pytest.mark.parametrize('D', [4, 6, 8])
 def test_cw_spline_and_log_norm(D):
     g = load_golden(f'cw_spline_d{D}')
