@@ -13,6 +13,7 @@
 #include "em_kernels.cuh"
 #include "em_persistent.cuh"
 #include "em_ws.cuh"
+#include "em_ls.cuh"
 #include "prof.cuh"
 
 #ifndef PBB_CTA_FPL
@@ -151,8 +152,20 @@ static int launch_normalize(const void* y, void* z, int F, int T, int D, int swa
   return 0;
 }
 
+// D = 8 lean fits run on em_ls_kernel (staged layout 1) unless PBB_EM_KERNEL=ws|single selects an older kernel
+static int em_kernel_choice() {
+  static const int c = [] {
+    const char* e = getenv("PBB_EM_KERNEL");
+    if (e == nullptr) return getenv("PBB_NO_WS") != nullptr ? 2 : 0;
+    if (!strcmp(e, "ws")) return 1;
+    if (!strcmp(e, "single")) return 2;
+    return 0;
+  }();
+  return c;  // 0 = em_ls_kernel, 1 = em_ws_kernel, 2 = em_persistent_kernel
+}
+static bool use_ls_kernel(int D, bool full) { return D == 8 && !full && em_kernel_choice() == 0; }
 template <typename CT>
-static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, int* dead, cudaStream_t st) {
+static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, int* dead, int layout, cudaStream_t st) {
   if (dead != nullptr) PBB_CUDA(cudaMemsetAsync(dead, 0, (size_t)F * sizeof(int), st));
   const int block = 64;  // divides kStageFrames
   const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
@@ -160,7 +173,8 @@ static int launch_normalize_staged(const void* y, void* z, int F, int T, int D, 
   const size_t smem = (size_t)block * (D + 1) * sizeof(double2);
   LaunchScope ls("normalize_staged_kernel", st);
   normalize_staged_kernel<CT><<<grid, block, smem, st>>>(reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), F, T, D,
-                                                          stage_rows(D), kStageFrames, nchunks, dead);
+                                                          layout == 0 ? stage_rows(D) : D, kStageFrames, nchunks, dead,
+                                                          layout);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -368,7 +382,8 @@ static int get_load_stream(LoadStream** out) {
 
 template <typename CT>
 static int launch_stream_load(const void* y, void* z, const double* aff_src, double* aff_dst, int F, int T, int D, int K,
-                              int* dead, int* flags, int* next_bin, int* started, int* ctas_out, cudaStream_t st) {
+                              int* dead, int* flags, int* next_bin, int* started, int* ctas_out, int layout,
+                              cudaStream_t st) {
   const int nchunks = (((T + 31) / 32 * 32) + kStageFrames - 1) / kStageFrames;
   const size_t smem = (size_t)kStageFrames * (D + 1) * sizeof(double2);
   LaunchScope ls("stream_load_kernel", st);
@@ -377,8 +392,8 @@ static int launch_stream_load(const void* y, void* z, const double* aff_src, dou
   ctas = ctas < F ? ctas : F;
   *ctas_out = ctas;
   stream_load_kernel<CT><<<ctas, kLoadThreads, smem, st>>>(
-      reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), aff_src, aff_dst, F, T, D, K, stage_rows(D),
-      kStageFrames, nchunks, dead, flags, next_bin, started);
+      reinterpret_cast<const CT*>(y), reinterpret_cast<CT*>(z), aff_src, aff_dst, F, T, D, K,
+      layout == 0 ? stage_rows(D) : D, kStageFrames, nchunks, dead, flags, next_bin, started, layout);
   PBB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -416,10 +431,13 @@ static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
     return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, 32 * (D / 2),
                                      sizeof(PersistSmem<D, K, CT>), &cache_full, a, "em_persistent_kernel", st);
   if constexpr (D == 8) {
-    // warp-specialised variant (em_ws.cuh): producer / EM / update warps with their own register budgets
-    static int cache_ws = 0;
-    static const bool no_ws = getenv("PBB_NO_WS") != nullptr;  // A/B switch
-    if (!no_ws)
+    // lane = slot variant (em_ls.cuh): one task per SM, 16 compute warps, no barrier in the hot loop
+    static int cache_ls = 0, cache_ws = 0;
+    if (em_kernel_choice() == 0)
+      return launch_persistent_generic(em_ls_kernel<K, CT>, kLsThreads, sizeof(LsSmem<K, CT>), &cache_ls, a,
+                                       "em_ls_kernel", st);
+    // warp-specialised variant of round 1 (em_ws.cuh): PBB_EM_KERNEL=ws
+    if (em_kernel_choice() == 1)
       return launch_persistent_generic(em_ws_kernel<K, CT>, 256, sizeof(WsSmem<D, K, CT>), &cache_ws, a,
                                        "em_ws_kernel", st);
   }
@@ -580,6 +598,11 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   }
   const bool streamed = persistent && y_host && init_aff != nullptr && !(opt->reserved & 2) &&
                         ws.aff_stage != nullptr;
+  const bool fast_sm = softmax_fast_ok(D, opt);
+  // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
+  const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
+  const bool full = saliency != nullptr || activity != nullptr || !lean_ok || init_aff == nullptr;
+  const int layout = persistent && use_ls_kernel(D, full) ? 1 : 0;
   if (streamed) {
     // flags[bin] = -1 until the bin has arrived
     PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
@@ -594,8 +617,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     int* started = reinterpret_cast<int*>(ws.phase + 14);
     int ctas = 0;
     r = dtype == PBB_C128
-            ? launch_stream_load<double2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, l->stream)
-            : launch_stream_load<float2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, l->stream);
+            ? launch_stream_load<double2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, layout, l->stream)
+            : launch_stream_load<float2>(y, ws.z, init_aff, aff_dst, F, T, D, K, ws.dead, ws.flags, next_bin, started, &ctas, layout, l->stream);
     if (r) return r;
     PBB_CUDA(cudaEventRecord(l->join, l->stream));
     // Hold the EM kernel back until every loader CTA runs: launched at the same moment, the EM grid
@@ -608,8 +631,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     }
     if (aff_host) init_aff = ws.aff_stage;
   } else if (persistent)  // chunk-major staged layout: one TMA bulk copy per ring stage
-    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)
-                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, st);
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, layout, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, layout, st);
   else
     r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
                           : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
@@ -635,7 +658,6 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   u.coef = ws.coef; u.ld = ws.ld; u.ew = ws.ew;
   u.status = status;
 
-  const bool fast_sm = softmax_fast_ok(D, opt);
   if (persistent) {
     // ---- persistent path: every EM iteration in one launch (em_persistent.cuh) ----
     if (!streamed)
@@ -682,9 +704,6 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
         if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
       }
     }
-    // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
-    const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
-    const bool full = saliency != nullptr || activity != nullptr || !lean_ok || p.user_model;
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
     if (streamed) {
       LoadStream* l = nullptr;
@@ -851,8 +870,8 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
   const bool persistent = fast_shape(D, K) && saliency == nullptr;
   int r;
   if (persistent)
-    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, st)
-                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, st);
+    r = dtype == PBB_C128 ? launch_normalize_staged<double2>(y, ws.z, F, T, D, ws.dead, 0, st)
+                          : launch_normalize_staged<float2>(y, ws.z, F, T, D, ws.dead, 0, st);
   else
     r = dtype == PBB_C128 ? launch_normalize<double2>(y, ws.z, F, T, D, 1, ws.zs, st)
                           : launch_normalize<float2>(y, ws.z, F, T, D, 1, ws.zs, st);
