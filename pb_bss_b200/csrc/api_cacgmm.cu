@@ -115,7 +115,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t o_flags = take((size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8);
   const size_t o_dead = take((size_t)F * sizeof(int));
   const size_t o_part = take((size_t)F * max_chunks(T) * K * (NS + 1) * sizeof(double));
-  const size_t o_coef = take((size_t)F * K * NS * sizeof(double));
+  const size_t o_coef = take((size_t)F * (K * NS + 8) * sizeof(double));  // em_ls.cuh model blocks: + 64 B per bin
   const size_t o_ld = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
   const size_t o_w = take((size_t)F * K * sizeof(double));
   const size_t o_ew = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
@@ -152,14 +152,16 @@ static int launch_normalize(const void* y, void* z, int F, int T, int D, int swa
   return 0;
 }
 
-// D = 8 lean fits run on em_ls_kernel (staged layout 1) unless PBB_EM_KERNEL=ws|single selects an older kernel
+// D = 8 lean fits run on em_ws_kernel.  PBB_EM_KERNEL=ls selects the round-2 lane = slot kernel (em_ls.cuh, staged
+// layout 1; measured 2.79 ms vs 2.38 ms on the C2 fit), PBB_EM_KERNEL=single (or PBB_NO_WS) the
+// single-role persistent kernel.
 static int em_kernel_choice() {
   static const int c = [] {
     const char* e = getenv("PBB_EM_KERNEL");
-    if (e == nullptr) return getenv("PBB_NO_WS") != nullptr ? 2 : 0;
-    if (!strcmp(e, "ws")) return 1;
+    if (e == nullptr) return getenv("PBB_NO_WS") != nullptr ? 2 : 1;
+    if (!strcmp(e, "ls")) return 0;
     if (!strcmp(e, "single")) return 2;
-    return 0;
+    return 1;
   }();
   return c;  // 0 = em_ls_kernel, 1 = em_ws_kernel, 2 = em_persistent_kernel
 }
@@ -600,7 +602,8 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
                         ws.aff_stage != nullptr;
   const bool fast_sm = softmax_fast_ok(D, opt);
   // lean variant: product-form softmax, needs (K-1) D log10(1/floor) < 290 (em_persistent.cuh)
-  const bool lean_ok = fast_sm && (K - 1) * D * log10(1.0 / opt->eigenvalue_floor) < 290.0;
+  // (one decade of margin per factor: em_ls.cuh scales the class matrices to trace [1, 2) instead of D)
+  const bool lean_ok = fast_sm && (K - 1) * D * (log10(1.0 / opt->eigenvalue_floor) + 1.0) < 290.0;
   const bool full = saliency != nullptr || activity != nullptr || !lean_ok || init_aff == nullptr;
   const int layout = persistent && use_ls_kernel(D, full) ? 1 : 0;
   if (streamed) {
@@ -712,16 +715,19 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
     }
 #ifdef PBB_PHASE_TIMING
     {
-      unsigned long long ph[12];
+      unsigned long long ph[16];
       cudaStreamSynchronize(st);
       cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[phase] update of class 0, cycles per task: build %.0f  gauss-jordan %.0f  logdet/tinv %.0f  stores %.0f\n",
               ph[8] / (double)((size_t)F * opt->iterations), ph[9] / (double)((size_t)F * opt->iterations),
               ph[10] / (double)((size_t)F * opt->iterations), ph[11] / (double)((size_t)F * opt->iterations));
+      fprintf(stderr, "[phase] producer, cycles per task: ticket->dependency %.0f  model buffer wait %.0f  model issue %.0f  ring refill %.0f\n",
+              ph[12] / (double)((size_t)F * opt->iterations), ph[13] / (double)((size_t)F * opt->iterations),
+              ph[14] / (double)((size_t)F * opt->iterations), ph[15] / (double)((size_t)F * opt->iterations));
       unsigned long long tot = 0;
       for (int i = 0; i < 8; ++i) tot += ph[i];
       static const char* nm[8] = {"ticket+flag / model wait", "chunk-top / updater busy", "tma-wait", "em-steps", "reduce", "update / S wait", "publish / hand-over", "task-start / updater idle"};
-      for (int i = 0; i < 8; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%\n", nm[i], 100.0 * ph[i] / (double)tot);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, "[phase] %-20s %6.2f%%  %8.0f cycles per task\n", nm[i], 100.0 * ph[i] / (double)tot, ph[i] / (double)((size_t)F * opt->iterations));
     }
 #endif
     u.nch = 1;  // the last iteration's raw scatter sums -> reference-exact model

@@ -359,8 +359,9 @@ def test_pinned_host_inputs_stream_in_and_match_device_inputs(shape, cdtype):
 
 
 def test_warp_specialised_and_single_role_kernels_agree(tmp_path):
-    """D = 8 fits run on em_ws_kernel (producer / EM / update warps); PBB_NO_WS=1 selects the single-role
-    persistent kernel.  Same tasks, same arithmetic except the order in which sum(gamma) is accumulated."""
+    """D = 8 fits run on em_ws_kernel (producer / EM / update warps); PBB_EM_KERNEL=single selects the single-role
+    persistent kernel, PBB_EM_KERNEL=ls the lane = slot kernel of round 2 (different summation order and an
+    exact power-of-two scaling of the class matrices instead of the trace normalisation)."""
     import os
     import subprocess
     import sys
@@ -376,7 +377,7 @@ def test_warp_specialised_and_single_role_kernels_agree(tmp_path):
         "    out['w%%d' %% K] = m.weight; out['c%%d' %% K] = m.cacg.covariance\n"
         "np.savez(sys.argv[1], **out)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     res = {}
-    for tag, env in (('ws', {}), ('single', {'PBB_NO_WS': '1'})):
+    for tag, env in (('ws', {}), ('single', {'PBB_EM_KERNEL': 'single'}), ('ls', {'PBB_EM_KERNEL': 'ls'})):
         path = str(tmp_path / f'{tag}.npz')
         e = dict(os.environ)
         e.update(env)
@@ -384,6 +385,7 @@ def test_warp_specialised_and_single_role_kernels_agree(tmp_path):
         res[tag] = np.load(path)
     for k in res['ws'].files:
         np.testing.assert_allclose(res['ws'][k], res['single'][k], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(res['ws'][k], res['ls'][k], rtol=1e-9, atol=1e-12)
 
 
 def test_argument_errors():
