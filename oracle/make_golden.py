@@ -286,9 +286,38 @@ def make_bf_wrapper(ref):
     np.savez_compressed(os.path.join(OUT, 'bf_wrapper.npz'), **out)
 
 
+def make_full_size(ref):
+    """BASELINE.json configs 2 and 4 at FULL size, outputs only (the seeded inputs are regenerated by the tests):
+    the fitted model on every bin and the affiliations of every bin at every 8th frame."""
+    T = ref.distribution.CACGMMTrainer
+    for name, gen in (('c2_full_noise', lambda: synth.noise_stft(513, 500, 8, seed=0)),
+                      ('c2_full_structured', lambda: synth.structured_stft(513, 500, 8, 3, seed=21)[0])):
+        y = gen()
+        init = synth.init_affiliation(513, 3, 500, seed=7)
+        model = T().fit(y, initialization=init, iterations=100)
+        aff = model.predict(y)
+        np.savez_compressed(
+            os.path.join(OUT, name + '.npz'), iterations=100,
+            weight=model.weight, eigenvalues=model.cacg.covariance_eigenvalues,
+            covariance=model.cacg.covariance, affiliation_8=aff[..., ::8],
+            log_likelihood=model.log_likelihood(y))
+    y = synth.noise_stft(257, 1000, 6, seed=4)
+    init = synth.init_affiliation(257, 4, 1000, seed=7)
+    model = ref.distribution.CWMMTrainer().fit(y, initialization=init, iterations=50)
+    aff = model.predict(y)
+    np.savez_compressed(
+        os.path.join(OUT, 'c4_full_noise.npz'), iterations=50, weight=model.weight,
+        mode=model.complex_watson.mode, concentration=model.complex_watson.concentration,
+        affiliation_8=aff[..., ::8])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'full':
+        make_full_size(ref)
+        return
     make_cacgmm(ref)
     make_cacgmm_coupled(ref)
     make_cacg_steps(ref)
@@ -298,6 +327,7 @@ def main():
     make_permutation_greedy_oracle(ref)
     make_beamformer(ref)
     make_bf_wrapper(ref)
+    make_full_size(ref)
     total = 0
     for n in sorted(os.listdir(OUT)):
         s = os.path.getsize(os.path.join(OUT, n))

@@ -107,7 +107,7 @@ int pbb_solve_batched(const void* a, const void* b, int n, int D, int R, int her
   PBB_CHECK_ARG(R > 0 && R <= 64, 5, "need 0 < R <= 64");
   PBB_CHECK_ARG(x != nullptr, 7, "x is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t per = ((size_t)(D * D + D * R) * sizeof(double2) + 15) & ~(size_t)15;
+  const size_t per = solve_smem_per_warp(D, R);
   const int warps = warps_for(per);
   PBB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   LaunchScope ls("solve_kernel", st);

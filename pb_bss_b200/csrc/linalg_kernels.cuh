@@ -147,15 +147,31 @@ __global__ void gev_kernel(const double2* __restrict__ a, const double2* __restr
     atomicMax(status, m + 1);
 }
 
+// shared memory of one warp of solve_kernel: A, X and -- when the minimum-norm fallback is available (D <= kLstsqMaxD)
+// -- a second matrix, the eigenvectors, a right-hand-side scratch and the Jacobi rotations
+constexpr int kLstsqMaxD = 40;
+__host__ __device__ inline size_t solve_smem_per_warp(int D, int R) {
+  size_t b = (size_t)(D * D + D * R) * sizeof(double2);
+  if (D <= kLstsqMaxD) b += (size_t)(2 * D * D + D * R) * sizeof(double2) + (size_t)((D + 1) / 2) * 6 * sizeof(double);
+  return (b + 15) & ~(size_t)15;
+}
+
 // ---- general complex solve A X = B with partial pivoting (np.linalg.solve / zgesv) ----
 // A (n, D, D), B (n, D, R) -> X (n, D, R).  hermitize: use (A + A^H) / 2 (beamformer.py:246-248).
+// An exactly singular system (zero pivot: LinAlgError in the reference) takes the reference's fallback,
+// np.linalg.lstsq (beamformer.py:251-256, math/solve.py:95-114): the minimum-norm solution X = A^+ B.  A Hermitian A
+// (the PSD matrices of this path) is pseudo-inverted through its eigendecomposition, eigenvalues below
+// eps * D * max|lambda| count as zero like LAPACK's rcond; a non-Hermitian A through A^H A (singular values below
+// ~1e-7 of the largest count as zero there).  An
+// all-zero A gives X = 0 (test_beamformer.py:211-376).  Non-finite input propagates as NaN, as it does in LAPACK.
+// status (may be null) is only set when the fallback is unavailable (D > kLstsqMaxD).
 __global__ void solve_kernel(const double2* __restrict__ a, const double2* __restrict__ b, int n, int D, int R,
                              int hermitize, double2* __restrict__ x, int* status, int warps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * warps + warp;
   if (m >= n) return;
-  const size_t per = ((size_t)(D * D + D * R) * sizeof(double2) + 15) & ~(size_t)15;
+  const size_t per = solve_smem_per_warp(D, R);
   double2* A = reinterpret_cast<double2*>(smem_raw + per * warp);
   double2* X = A + D * D;
   const double2* __restrict__ am = a + (size_t)m * D * D;
@@ -171,7 +187,7 @@ __global__ void solve_kernel(const double2* __restrict__ a, const double2* __res
   }
   for (int i = lane; i < D * R; i += 32) X[i] = b[(size_t)m * D * R + i];
   __syncwarp();
-  bool singular = false;
+  bool singular = false, nonfinite = false;
   for (int j = 0; j < D; ++j) {
     // pivot search (every lane redundantly: D is tiny)
     int piv = j;
@@ -181,7 +197,8 @@ __global__ void solve_kernel(const double2* __restrict__ a, const double2* __res
       const double mag = fabs(v.x) + fabs(v.y);  // LAPACK izamax uses |re| + |im|
       if (mag > best) { best = mag; piv = i; }
     }
-    if (!(best > 0.0) || !isfinite(best)) { singular = true; break; }
+    if (!isfinite(best)) { nonfinite = true; break; }
+    if (!(best > 0.0)) { singular = true; break; }
     if (piv != j) {
       for (int c = lane; c < D; c += 32) { const double2 t = A[j * D + c]; A[j * D + c] = A[piv * D + c]; A[piv * D + c] = t; }
       for (int c = lane; c < R; c += 32) { const double2 t = X[j * R + c]; X[j * R + c] = X[piv * R + c]; X[piv * R + c] = t; }
@@ -205,7 +222,10 @@ __global__ void solve_kernel(const double2* __restrict__ a, const double2* __res
     }
     __syncwarp();
   }
-  if (!singular) {
+  if (nonfinite) {
+    for (int i = lane; i < D * R; i += 32) X[i] = make_double2(NAN, NAN);
+    __syncwarp();
+  } else if (!singular) {
     for (int c = lane; c < R; c += 32) {  // back substitution, columns in parallel
       for (int i = D - 1; i >= 0; --i) {
         double2 s = X[i * R + c];
@@ -217,8 +237,90 @@ __global__ void solve_kernel(const double2* __restrict__ a, const double2* __res
       }
     }
     __syncwarp();
-  } else if (lane == 0 && status) {
-    atomicMax(status, m + 1);
+  } else if (D > kLstsqMaxD) {
+    if (lane == 0 && status) atomicMax(status, m + 1);
+  } else {
+    // ---- minimum-norm least squares (np.linalg.lstsq) ----
+    double2* G = X + D * R;          // matrix to diagonalise
+    double2* V = G + D * D;          // its eigenvectors
+    double2* Y = V + D * D;          // right-hand side in the eigenbasis
+    double* rot = reinterpret_cast<double*>(Y + D * R);
+    double asym = 0.0, amax = 0.0;
+    for (int i = lane; i < D * D; i += 32) {
+      const int r = i / D, c = i - r * D;
+      double2 u = am[i];
+      const double2 v = am[c * D + r];
+      if (hermitize) u = make_double2(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+      A[i] = u;
+      asym = fmax(asym, hermitize ? 0.0 : fabs(u.x - v.x) + fabs(u.y + v.y));
+      amax = fmax(amax, fabs(u.x) + fabs(u.y));
+    }
+    for (int i = lane; i < D * R; i += 32) X[i] = b[(size_t)m * D * R + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      asym = fmax(asym, __shfl_xor_sync(0xffffffffu, asym, o));
+      amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    __syncwarp();
+    const bool herm = asym <= 1e-14 * amax;
+    // G = A (Hermitian) or A^H A; Y0 = B or A^H B
+    for (int i = lane; i < D * D; i += 32) {
+      const int r = i / D, c = i - r * D;
+      double2 g = A[i];
+      if (!herm) {
+        g = make_double2(0.0, 0.0);
+        for (int k = 0; k < D; ++k) {
+          const double2 q = cmulc(A[k * D + c], A[k * D + r]);  // conj(A[k][r]) * A[k][c]
+          g.x += q.x; g.y += q.y;
+        }
+      }
+      G[i] = g;
+    }
+    for (int i = lane; i < D * R; i += 32) {
+      const int r = i / R, c = i - r * R;
+      double2 y = X[i];
+      if (!herm) {
+        y = make_double2(0.0, 0.0);
+        for (int k = 0; k < D; ++k) {
+          const double2 q = cmulc(X[k * R + c], A[k * D + r]);  // conj(A[k][r]) * B[k][c]
+          y.x += q.x; y.y += q.y;
+        }
+      }
+      Y[i] = y;
+    }
+    __syncwarp();
+    warp_jacobi_any(G, V, rot, D, lane);
+    __syncwarp();
+    double lmax = 0.0;
+    for (int i = 0; i < D; ++i) lmax = fmax(lmax, fabs(G[i * D + i].x));
+    const double cut = (herm ? 1.0 : 8.0) * DBL_EPSILON * D * lmax;
+    // X = V diag(1 / lambda) V^H Y0 over the eigenvalues above the cut-off
+    for (int i = lane; i < D * R; i += 32) {  // T = diag^+ V^H Y0, stored in X
+      const int e = i / R, c = i - e * R;
+      const double l = G[e * D + e].x;
+      double2 t = make_double2(0.0, 0.0);
+      if (fabs(l) > cut) {
+        for (int k = 0; k < D; ++k) {
+          const double2 q = cmulc(Y[k * R + c], V[k * D + e]);  // conj(V[k][e]) * Y0[k][c]
+          t.x += q.x; t.y += q.y;
+        }
+        t.x /= l; t.y /= l;
+      }
+      X[i] = t;
+    }
+    __syncwarp();
+    for (int i = lane; i < D * R; i += 32) {
+      const int r = i / R, c = i - r * R;
+      double2 o = make_double2(0.0, 0.0);
+      for (int e = 0; e < D; ++e) {
+        const double2 q = cmul(V[r * D + e], X[e * R + c]);
+        o.x += q.x; o.y += q.y;
+      }
+      Y[i] = o;
+    }
+    __syncwarp();
+    for (int i = lane; i < D * R; i += 32) X[i] = Y[i];
+    __syncwarp();
   }
   for (int i = lane; i < D * R; i += 32) x[(size_t)m * D * R + i] = X[i];
 }

@@ -117,9 +117,11 @@ def get_mvdr_vector(atf_vector, noise_psd_matrix):
     lib = _lib.load()
     _lib.check(lib.pbb_mvdr(_device.ptr(atf_f), _device.ptr(noise_f), n, D, _device.ptr(w),
                             _device.ptr(scratch), _device.ptr(status), _device.stream_ptr()), 'pbb_mvdr')
+    # a singular noise PSD matrix takes the reference's np.linalg.lstsq fallback (beamformer.py:251-256) on the
+    # device (minimum-norm solution); the status word is only set where that fallback does not exist (D > 40)
     s = int(status.item())
     if s:
-        raise np.linalg.LinAlgError(f'get_mvdr_vector: singular noise PSD matrix {s - 1}')
+        raise np.linalg.LinAlgError(f'get_mvdr_vector: singular noise PSD matrix {s - 1} (D > 40: no lstsq fallback)')
     return _device.to_host(w.reshape(*lead, D), like_numpy)
 
 
@@ -159,6 +161,12 @@ def get_mvdr_vector_souden(target_psd_matrix, noise_psd_matrix, ref_channel=None
     """Souden MVDR, beamformer.py:627-698 (+ get_optimal_reference_channel :601-624)."""
     assert noise_psd_matrix is not None
     like_numpy = not _device.is_tensor(target_psd_matrix)
+    if isinstance(target_psd_matrix, (list, tuple)):
+        target_psd_matrix = np.asarray(target_psd_matrix)
+    if isinstance(noise_psd_matrix, (list, tuple)):
+        noise_psd_matrix = np.asarray(noise_psd_matrix)
+    # real PSD matrices give a real vector in the reference (NumPy keeps the dtype); the device path is complex
+    real_in = like_numpy and not np.iscomplexobj(target_psd_matrix) and not np.iscomplexobj(noise_psd_matrix)
     t = _device.to_device(np.asarray(target_psd_matrix) if isinstance(target_psd_matrix, (list, tuple))
                           else target_psd_matrix, torch.complex128)
     nz = _device.to_device(np.asarray(noise_psd_matrix) if isinstance(noise_psd_matrix, (list, tuple))
@@ -175,9 +183,10 @@ def get_mvdr_vector_souden(target_psd_matrix, noise_psd_matrix, ref_channel=None
     status.zero_()
     _lib.check(lib.pbb_solve_batched(_device.ptr(nf), _device.ptr(tf), n, D, D, 0, _device.ptr(phi),
                                      _device.ptr(status), _device.stream_ptr()), 'pbb_solve_batched')
+    # stable_solve (math/solve.py:95-114): singular systems get the minimum-norm (lstsq) solution on the device
     s = int(status.item())
     if s:
-        raise np.linalg.LinAlgError(f'get_mvdr_vector_souden: singular noise PSD matrix {s - 1}')
+        raise np.linalg.LinAlgError(f'get_mvdr_vector_souden: singular noise PSD matrix {s - 1} (D > 40: no lstsq fallback)')
     mat = _device.empty((n, D, D), torch.complex128)
     num = _device.empty((n, D), torch.complex128)
     den = _device.empty((n, D), torch.complex128)
@@ -198,6 +207,8 @@ def get_mvdr_vector_souden(target_psd_matrix, noise_psd_matrix, ref_channel=None
         ref_channel = int(np.argmax(snr.real))
     assert np.isscalar(ref_channel), ref_channel
     beamformer = _device.to_host(mat[..., ref_channel].reshape(*lead, D).contiguous(), like_numpy)
+    if real_in:
+        beamformer = np.ascontiguousarray(beamformer.real)
     return (beamformer, ref_channel) if return_ref_channel else beamformer
 
 

@@ -93,10 +93,14 @@ def test_error_paths():
     b[1] = -np.eye(D)  # not positive definite
     with pytest.raises(ValueError):
         E.get_gev_vector(a, b)
+    # a singular noise PSD no longer raises: like the reference (beamformer.py:251-256) the bin takes the lstsq
+    # fallback; an all-zero matrix gives 0 / 0 there and leaves the other bins untouched
     sing = a.copy()
     sing[2] = 0
-    with pytest.raises(np.linalg.LinAlgError):
-        E.get_mvdr_vector(np.ones((3, D), dtype=np.complex128), sing)
+    atf = np.ones((3, D), dtype=np.complex128)
+    w = E.get_mvdr_vector(atf, sing)
+    assert np.all(np.isnan(w[2])) and np.all(np.isfinite(w[:2]))
+    np.testing.assert_allclose(w[:2], O.mvdr_vector(atf[:2], sing[:2]), rtol=1e-9)
     with pytest.raises(NotImplementedError):
         E.get_gev_vector(a, a, use_eig=True)
 
@@ -141,3 +145,64 @@ def test_rank_one_estimates_match_reference_golden():
     with pytest.raises(ValueError):
         from pb_bss_b200.extraction import get_bf_vector
         get_bf_vector('nonsense', g['target'], g['noise'])
+
+
+class _Souden:
+    """Fixture of tests/test_extraction/test_beamformer.py:185-203 of the reference."""
+    obs = np.array([[0, 0, 1], [0, 0.1, 1], [0.1, 0, 1]])
+    PhiXX = obs.T.conj() @ obs          # real, like the reference's fixture
+    PhiNN = np.eye(3)
+    well = np.array([0.03311258, 0.03311258, 0.99337748])
+
+
+def test_souden_difficulties_like_the_reference():
+    """The reference pins the behaviour of get_mvdr_vector_souden on zero / inf PSD matrices
+    (tests/test_extraction/test_beamformer.py:211-376): zeros give a zero vector (stable_solve's lstsq fallback,
+    math/solve.py:95-114), infinities an AssertionError, and with eps = 0 every broken bin is an AssertionError."""
+    from pb_bss_b200.extraction import get_mvdr_vector_souden as souden
+    X, N = _Souden.PhiXX, _Souden.PhiNN
+    with np.errstate(all='ignore'):
+        for args in ((X[None] * 0, N[None]), (X[None], N[None] * 0), (X[None] * 0, N[None] * 0)):
+            w = souden(*args)
+            assert repr(w) == 'array([[0., 0., 0.]])', repr(w)
+        for args in ((X[None] * np.inf, N[None]), (X[None], N[None] * np.inf), (X[None] * np.inf, N[None] * np.inf)):
+            with pytest.raises(AssertionError):
+                souden(*args)
+        # eps = 0, single bin: everything broken is an AssertionError
+        for args in ((X[None] * 0, N[None]), (X[None], N[None] * 0), (X[None] * 0, N[None] * 0),
+                     (X[None] * np.inf, N[None]), (X[None], N[None] * np.inf), (X[None] * np.inf, N[None] * np.inf)):
+            with pytest.raises(AssertionError):
+                souden(*args, eps=0)
+        # several bins: zero bins only damage themselves
+        for args in (([X * 0, X], [N, N]), ([X, X], [N * 0, N]), ([X * 0, X], [N * 0, N])):
+            w, ref_channel = souden(np.array(args[0]), np.array(args[1]), return_ref_channel=True)
+            assert ref_channel == 2, ref_channel
+            np.testing.assert_allclose(w, np.array([[0., 0., 0.], _Souden.well]), atol=1e-8)
+        for args in (([X * np.inf, X], [N, N]), ([X, X], [N * np.inf, N]), ([X * np.inf, X], [N * np.inf, N])):
+            with pytest.raises(AssertionError):
+                souden(np.array(args[0]), np.array(args[1]), return_ref_channel=True)
+        for args in (([X * 0, X], [N, N]), ([X, X], [N * 0, N]), ([X * 0, X], [N * 0, N]),
+                     ([X * np.inf, X], [N, N]), ([X, X], [N * np.inf, N]), ([X * np.inf, X], [N * np.inf, N])):
+            with pytest.raises(AssertionError):
+                souden(np.array(args[0]), np.array(args[1]), eps=0, return_ref_channel=True)
+
+
+def test_singular_systems_take_the_minimum_norm_solution():
+    """pbb_solve_batched against np.linalg.lstsq (what stable_solve falls back to, math/solve.py:111-113) on exactly
+    singular matrices: a zero matrix, a Hermitian PSD matrix of rank 2, a general matrix with a zero row."""
+    from pb_bss_b200.extraction.linalg import solve
+    rng = np.random.RandomState(3)
+    D = 6
+    A = synth.pos_def_hermitian(5, D, D, seed=2)
+    B = rng.randn(5, D, D) + 1j * rng.randn(5, D, D)
+    A[1] = 0
+    v = rng.randn(D, 2) + 1j * rng.randn(D, 2)
+    A[2] = v @ v.conj().T                      # rank 2: elimination meets an exactly zero pivot only by luck ...
+    A[2][:, 3:] = 0; A[2][3:, :] = 0           # ... so make the deficiency exact
+    G = rng.randn(D, D) + 1j * rng.randn(D, D)
+    G[4] = 0                                   # non-Hermitian, zero row
+    A[3] = G
+    X = solve(A, B)
+    for i in range(5):
+        ref = np.linalg.lstsq(A[i], B[i], rcond=None)[0]
+        np.testing.assert_allclose(X[i], ref, rtol=1e-7, atol=1e-9, err_msg=f'system {i}')
