@@ -12,10 +12,12 @@ N > 1 (torchrun, one rank per GPU): every rank fits its own utterance of the
 same shape (the path shards over independent utterances / bins without any
 data-path collective) -> "scaling": "weak"; value is the whole-job aggregate.
 
-Keys beyond the base contract: `roofline` (dominant kernel vs measured HBM
-peak), `cpu_baseline` (the NumPy oracle port timed on this host, rank 0, N=1),
-`e2e` (same metric through the public API with HOST buffers, H2D/D2H inside
-the timed region), `frames_bins_per_s`, `clocks`, `gpu_launches`.
+Keys beyond the base contract: `roofline` (dominant kernel vs the measured HBM peak, plus the fp64-pipe
+fractions that actually bound it), `cpu_baseline` (the reference -- oracle/_ref, else the NumPy port -- timed on this
+host, rank 0, N=1), `e2e` (same metric through the public API with pinned HOST tensors, H2D/D2H inside the timed
+region), `e2e_numpy` (the drop-in call: NumPy arrays in, NumPy model out, pageable copies inside the timed region),
+`c3_bin_sharded` (BASELINE.json config 3: ONE utterance, bins sharded over the N ranks, fit + predict + all-gather +
+DHTV + PSD + GEV + apply, per-stage device times), `frames_bins_per_s`, `clocks`, `gpu_launches`.
 """
 import argparse
 import json
@@ -108,65 +110,190 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------
-# CPU baseline: the NumPy oracle port (same einsums as the reference)
+# CPU baseline: the unmodified reference (oracle/_ref, see oracle/build_ref.py) when it travelled with the
+# repository, else the NumPy oracle port (same einsums as the reference)
 # --------------------------------------------------------------------------
-def _cpu_fit_worker(args):
-    y, init, iters = args
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+def _cpu_fit_fn():
+    """Returns (fit(y, init, iterations), kind, description)."""
+    try:
+        from oracle import ref_shim
+        if ref_shim.available():
+            ref = ref_shim.load()
+            trainer = ref.distribution.CACGMMTrainer()
+            return (lambda y, init, it: trainer.fit(y, initialization=init, iterations=it),
+                    'reference', 'pb_bss.distribution.CACGMMTrainer.fit of the unmodified reference (oracle/_ref)')
+    except Exception:
+        pass
     from oracle import pb_bss_oracle as O
-    t0 = time.perf_counter()
-    O.cacgmm_fit(y, init, iters)
-    return time.perf_counter() - t0
+    return (lambda y, init, it: O.cacgmm_fit(y, init, it)), 'port', 'oracle/pb_bss_oracle.cacgmm_fit (NumPy port)'
 
 
 def cpu_baseline_single(iters=40):
     """As shipped: one process (the hot einsums are single threaded)."""
-    from oracle import pb_bss_oracle as O
+    fit, kind, what = _cpu_fit_fn()
     y, init = _inputs(0)
-    O.cacgmm_fit(y[:32], init[:32], 2)  # warm-up (imports, einsum paths)
+    fit(y[:32], init[:32], 2)  # warm-up (imports, einsum paths)
     t0 = time.perf_counter()
-    O.cacgmm_fit(y, init, iters)
+    fit(y, init, iters)
     dt = time.perf_counter() - t0
-    return {'value': iters / dt, 'unit': 'EM iterations/s', 'cores': 1, 'kind': 'port',
-            'sample': f'{iters} EM iterations of the full C2 problem in {dt:.1f} s, oracle/pb_bss_oracle.cacgmm_fit, 1 process'}
+    return {'value': iters / dt, 'unit': 'EM iterations/s', 'cores': 1, 'kind': kind,
+            'sample': f'{iters} EM iterations of the full C2 problem in {dt:.1f} s, {what}, 1 process'}
+
+
+def _ref_worker(idx, cpu, lo, hi, conn):
+    """Persistent worker of the reference arm: owns bins [lo, hi) for the whole run (nothing is pickled per step),
+    pinned to one core, one BLAS thread."""
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    fit, kind, what = _cpu_fit_fn()
+    y, init = _inputs(0)
+    y, init = np.ascontiguousarray(y[lo:hi]), np.ascontiguousarray(init[lo:hi])
+    conn.send((kind, what))
+    while True:
+        iters = conn.recv()
+        if iters is None:
+            break
+        t0 = time.perf_counter()
+        fit(y, init, iters)
+        conn.send(time.perf_counter() - t0)
 
 
 def reference_arm(args):
-    """--impl reference: the CPU implementation with all host cores: the bins
-    are sharded over one worker process per core (bins are independent), wall
-    time of the slowest worker."""
+    """--impl reference: the reference's CPU implementation with all host cores.  The bins are independent, so they
+    are sharded over one persistent worker process per core; a step is one fit of the whole C2 problem (wall time of
+    the slowest worker), 100 EM iterations when the run then still ends within a few minutes, else a bounded sample."""
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, F))
-    iters = 10  # bounded sample per step
-    y, init = _inputs(0)
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cpus = list(range(os.cpu_count() or 1))
+    workers = max(1, min(len(cpus), F))
     bounds = np.linspace(0, F, workers + 1).astype(int)
-    jobs = [(y[a:b], init[a:b], iters) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
     ctx = mp.get_context('fork')
-    with ctx.Pool(len(jobs)) as pool:
-        for _ in range(max(1, args.warmup)):
-            pool.map(_cpu_fit_worker, [(j[0], j[1], 2) for j in jobs])
+    procs = []
+    for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+        if hi <= lo:
+            continue
+        pc, cc = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(i, cpus[i % len(cpus)], int(lo), int(hi), cc), daemon=True)
+        p.start()
+        procs.append((p, pc))
+    kind, what = procs[0][1].recv()
+    for _, pc in procs[1:]:
+        pc.recv()
+
+    def step(iters):
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_cpu_fit_worker, jobs)
-        dt = time.perf_counter() - t0
+        for _, pc in procs:
+            pc.send(iters)
+        for _, pc in procs:
+            pc.recv()
+        return time.perf_counter() - t0
+
+    step(2)
+    t_it = step(4) / 4  # seconds per EM iteration of the whole problem
+    budget = 150.0
+    iters = ITERS if (args.steps + max(1, args.warmup)) * ITERS * t_it <= budget else \
+        max(4, int(budget / ((args.steps + max(1, args.warmup)) * t_it)))
+    for _ in range(max(1, args.warmup)):
+        step(iters)
+    ts = [step(iters) for _ in range(args.steps)]
+    for p, pc in procs:
+        pc.send(None)
+    for p, _ in procs:
+        p.join(timeout=5)
+    dt = sum(ts)
     value = args.steps * iters / dt
+    cfg = _config(args.gpus)
+    cfg['iterations_per_step'] = iters
+    cfg['parallelism'] = f'{len(procs)} worker processes, one per host core, bins sharded, no communication'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'EM iterations/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt / args.steps * 1e3 * (ITERS / iters), 'higher_is_better': True,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': max(1, args.warmup),
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': _config(args.gpus), 'frames_bins_per_s': value * F * T,
-        'cpu_baseline': {'value': value, 'unit': 'EM iterations/s', 'cores': len(jobs), 'kind': 'port',
-                         'sample': f'{iters} EM iterations per step of the full C2 problem, bins sharded over '
-                                   f'{len(jobs)} worker processes (oracle/pb_bss_oracle.cacgmm_fit); '
-                                   'ms_per_step is scaled to the 100-iteration fit'},
+        'config': cfg, 'frames_bins_per_s': value * F * T,
+        'step_spread': {'min_ms': min(ts) * 1e3, 'max_ms': max(ts) * 1e3},
+        'cpu_baseline': {'value': value, 'unit': 'EM iterations/s', 'cores': len(procs), 'kind': kind,
+                         'sample': f'{iters} EM iterations per step of the full C2 problem (F=513 bins sharded over '
+                                   f'{len(procs)} persistent worker processes pinned to one core each), {what}'},
         'e2e': {'value': value, 'unit': 'EM iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# BASELINE.json config 3: one utterance, bins sharded over the ranks
+# --------------------------------------------------------------------------
+def c3_bin_sharded_block(world, rank, barrier, reps=5):
+    """fit (100 it) + predict + all-gather + DHTV + PSD + GEV + apply on ONE utterance whose 513 bins are sharded
+    over the `world` ranks (pb_bss_b200.parallel.sharded_separation).  Device-timed with CUDA events per stage, max
+    over ranks; rank 0 also runs the whole utterance alone in the same job, which gives the speed-up."""
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    from pb_bss_b200 import parallel
+    y, _ = synth.structured_stft(F, T, D, K, seed=5)
+    init = synth.init_affiliation(F, K, T, seed=7)
+    lo, hi = parallel.bin_shards(F, world)[rank]
+    yl, il = torch.from_numpy(y[lo:hi]).cuda(), torch.from_numpy(init[lo:hi]).cuda()
+
+    def run(y_, i_, alone):
+        saved = parallel.world
+        if alone:
+            parallel.world = lambda group=None: (0, 1)
+        try:
+            best = None
+            for rep in range(reps + 2):
+                if not alone:
+                    barrier()
+                else:
+                    torch.cuda.synchronize()
+                tm = parallel.StageTimer()
+                parallel.sharded_separation(y_, i_, F, iterations=ITERS, timer=tm)
+                torch.cuda.synchronize()
+                ms = tm.ms()
+                ms['total'] = sum(ms.values())
+                if rep >= 2 and (best is None or ms['total'] < best['total']):
+                    best = ms
+            return best
+        finally:
+            parallel.world = saved
+
+    stages = run(yl, il, alone=False)
+    names = list(stages)
+    t = torch.tensor([stages[n] for n in names], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    stages = dict(zip(names, t.tolist()))
+    single = None
+    if rank == 0:
+        single = stages if world == 1 else run(torch.from_numpy(y).cuda(), torch.from_numpy(init).cuda(), alone=True)
+    if world > 1:
+        barrier()
+    if rank != 0:
+        return None
+    return {
+        'workload': 'C3: one utterance F=513 T=500 D=8 K=3 (structured mixture), bins sharded over the ranks; '
+                    'cACGMM fit 100 iterations + predict + NCCL all-gather of the affiliations + DHTV permutation '
+                    'alignment (replicated) + PSD + GEV + apply',
+        'n_gpus': world, 'bins_per_rank': [h - l for l, h in parallel.bin_shards(F, world)],
+        'ms_per_pipeline': stages['total'], 'stage_ms': {k: v for k, v in stages.items() if k != 'total'},
+        'single_gpu_ms_same_run': single['total'], 'single_gpu_stage_ms': {k: v for k, v in single.items() if k != 'total'},
+        'speedup_vs_single_gpu': single['total'] / stages['total'],
+        'timing': 'CUDA events on the launching stream, best of %d repetitions after 2 warm-ups, max over ranks per '
+                  'stage' % reps,
+    }
 
 
 # --------------------------------------------------------------------------
@@ -209,6 +336,12 @@ def b200_arm(args):
         assert not out[1].is_cuda
         return out
 
+    def step_numpy():
+        # the drop-in call of the reference's API: NumPy arrays in, NumPy model out (pageable host memory)
+        m = trainer.fit(y_host, initialization=init_host, iterations=ITERS)
+        assert isinstance(m.cacg.covariance_eigenvectors, np.ndarray)
+        return m
+
     for _ in range(max(3, args.warmup)):
         step_resident()
     barrier()
@@ -234,6 +367,15 @@ def b200_arm(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    step_numpy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_numpy()
+    torch.cuda.synchronize()
+    t_np = time.perf_counter() - t0
+    barrier()
+    c3 = c3_bin_sharded_block(world, rank, barrier)
     # the end-to-end path must produce the resident path's model (checked outside the timed regions)
     m_res = step_resident()
     out_e2e = step_e2e()
@@ -253,10 +395,10 @@ def b200_arm(args):
         lib.pbb_profile_enable(0)
         prof = {'kernel': name.value.decode(), 'ms_total': ms.value, 'launches': n.value}
 
-    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device='cuda')
+    times = torch.tensor([t_dev, t_e2e, t_np], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = times.tolist()
+    t_dev, t_e2e, t_np = times.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -264,6 +406,7 @@ def b200_arm(args):
 
     value = world * args.steps * ITERS / t_dev
     e2e = world * args.steps * ITERS / t_e2e
+    e2e_np = world * args.steps * ITERS / t_np
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -274,6 +417,7 @@ def b200_arm(args):
     # algorithmic bytes of one EM iteration (complex128):
     # F*T*D*16 + 2*F*K*(D*D*16 + D*8 + 8)
     b_iter = F * T * D * 16 + 2 * F * K * (D * D * 16 + D * 8 + 8)
+    line_clocks = clocks.summary()
     roofline = None
     traffic = None
     try:  # DRAM bytes of the same kernel + workload from the committed `ncu --set full` capture
@@ -290,8 +434,26 @@ def b200_arm(args):
                     'kernel': prof['kernel'], 'kernel_launches_per_fit': prof['launches'],
                     'kernel_ms_per_fit': prof['ms_total'],
                     'algorithmic_bytes_per_em_iteration': b_iter,
-                    'note': 'fp64 CUDA-core bound (2.8 kflop per frame*bin): the observation is L2 resident '
-                            'after the first iteration, so DRAM traffic is far below the algorithmic bytes'}
+                    'note': 'fp64 CUDA-core bound: the observation is L2 resident after the first iteration, so DRAM '
+                            'traffic is far below the algorithmic bytes; the fp64 figures below are the binding ones'}
+        # fp64 pipe: 560 pipe operations per frame x bin x iteration (512 slot-form E/M operations + posterior),
+        # DESIGN.md section 4.  Two denominators: the nominal DFMA rate (64 lanes/clk/SM: fma(a, x, y) with two
+        # operands held in the reuse cache, scripts/microbench/fp64_rate.cu) and the rate of a DFMA that reads three
+        # different 64-bit registers, which is what acc = fma(w, psi, acc) is (42.7 lanes/clk/SM measured,
+        # scripts/microbench/fp64_operands.cu, profiles/fp64_operands_r2.txt).
+        clk = (line_clocks or {}).get('sm_mhz') or 1965.0
+        ops = 560.0 * F * ((T + 31) // 32 * 32) * ITERS
+        t_k = prof['ms_total'] * 1e-3
+        nominal = 148 * 64 * clk * 1e6
+        roofline['fp64'] = {
+            'pipe_ops_per_launch': ops, 'achieved_lane_ops_per_s': ops / t_k,
+            'peak_nominal_lane_ops_per_s': nominal, 'frac_of_nominal_dfma_peak': ops / t_k / nominal,
+            'peak_three_register_dfma_lane_ops_per_s': nominal * 42.7 / 64,
+            'frac_of_three_register_dfma_peak': ops / t_k / (nominal * 42.7 / 64),
+            'sm_mhz': clk,
+            'chain_bound': 'one bin-iteration (task -> class update -> publish -> next model) has a latency of ~17 us '
+                           'on an otherwise idle GPU (profiles/chain_latency_r2.txt), which alone bounds a '
+                           '100-iteration fit at 1.7 ms whatever the arithmetic rate'}
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_baseline_single()
@@ -310,8 +472,14 @@ def b200_arm(args):
                             'read over PCIe by a loader kernel that overlaps the EM kernel, the model is '
                             'written to pinned host memory by the final update kernel; timed with the host '
                             'clock around K calls, each synchronised'},
+        'e2e_numpy': {'value': e2e_np, 'unit': 'EM iterations/s', 'ms_per_step': t_np / args.steps * 1e3,
+                      'h2d_bytes_per_step': int(y_host.nbytes + init_host.nbytes),
+                      'd2h_bytes_per_step': int(F * K * (D * D * 16 + D * 8 + 8)),
+                      'transfer': 'CACGMMTrainer.fit(numpy, initialization=numpy) -> model of NumPy arrays: pageable '
+                                  'host -> device copies, fit, device -> host copies, all inside the timed region'},
+        'c3_bin_sharded': c3,
         'gpu_launches': int(launches),
-        'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks.summary(),
+        'roofline': roofline, 'cpu_baseline': cpu, 'clocks': line_clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -13,6 +13,11 @@ import types
 import warnings
 
 REF = os.environ.get('PB_BSS_REFERENCE', '/root/reference')
+if not os.path.isdir(os.path.join(REF, 'pb_bss')):
+    # the GPU box has no checkout: the verbatim copy made by oracle/build_ref.py travels with the repository
+    _vendored = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+    if os.path.isdir(os.path.join(_vendored, 'pb_bss')):
+        REF = _vendored
 
 
 def available():

@@ -216,7 +216,12 @@ class CACGMMTrainer:
             assert initialization.ndim == len(shape), (initialization.shape, shape)
             assert tuple(initialization.shape[-2:]) == shape[-2:], (initialization.shape, shape)
             init_dev = _device.to_device(initialization, torch.float64, keep_pinned=yd.device.type == 'cpu')
-            init_dev = init_dev.expand(shape).reshape(F, K, N).contiguous()
+            init_dev = init_dev.expand(shape).reshape(F, K, N)
+            if not init_dev.is_contiguous():
+                # broadcast singleton dims materialise a new tensor: keep it where the library can read it
+                init_dev = init_dev.contiguous()
+                if init_dev.device.type == 'cpu':
+                    init_dev = init_dev.pin_memory()
         else:
             raise TypeError('No sufficient initialization.')
         assert K < 20, f'num_classes: {K}, sure?'

@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['world', 'bin_shards', 'local_bins', 'all_gather_bins',
-           'mean_over_all_bins', 'sharded_separation']
+           'mean_over_all_bins', 'sharded_separation', 'StageTimer']
 
 
 def world(group=None):
@@ -85,9 +85,27 @@ def mean_over_all_bins(local_mean, n_local, F, group=None):
     return total / float(F)
 
 
+class StageTimer:
+    """CUDA events between the stages of a pipeline (current stream); ``ms()`` after a synchronize."""
+
+    def __init__(self):
+        self.names, self.events = [], []
+        self.mark('start')
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.names.append(name)
+        self.events.append(e)
+
+    def ms(self):
+        return {n: self.events[i - 1].elapsed_time(self.events[i])
+                for i, n in enumerate(self.names) if i > 0}
+
+
 def sharded_separation(y_local, initialization_local, F, *, iterations=100,
                        stft_size=None, beamformer='gev', group=None,
-                       trainer_kwargs=None):
+                       trainer_kwargs=None, timer=None):
     """BASELINE.json config 3 on this rank's bin slice.
 
     cACGMM fit + predict on the local bins -> all-gather of the affiliations
@@ -99,8 +117,12 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
     initialization_local: (F_rank, K, T).  Returns a dict with the local
     ``model``, ``affiliation`` (aligned, (F_rank, K, T)), the global
     ``mapping`` (K, F), ``vectors`` (F_rank, K, D) and ``enhanced``
-    (F_rank, K, T).
+    (F_rank, K, T).  ``timer``: optional StageTimer, marked after every stage.
     """
+    def mark(name):
+        if timer is not None:
+            timer.mark(name)
+
     from .distribution import CACGMMTrainer
     from .extraction import (apply_beamforming_vector, get_gev_vector,
                              get_mvdr_vector, get_pca_vector,
@@ -111,8 +133,11 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
     assert y_local.shape[0] == hi - lo, (y_local.shape, (lo, hi))
     model = CACGMMTrainer().fit(y_local, initialization=initialization_local,
                                 iterations=iterations, **(trainer_kwargs or {}))
+    mark('fit')
     aff_local = model.predict(y_local)                       # (F_rank, K, T)
+    mark('predict')
     aff = all_gather_bins(aff_local, F, group)               # the one collective
+    mark('all_gather')
     if stft_size is None:
         stft_size = 2 * (F - 1)
     aligner = DHTVPermutationAlignment.from_stft_size(stft_size)
@@ -120,8 +145,10 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
     mapping = aligner.calculate_mapping(mask_kft)            # replicated, identical on all ranks
     aligned = apply_mapping(mask_kft[:, lo:hi].contiguous(), mapping[:, lo:hi].contiguous())
     aligned = aligned.permute(1, 0, 2).contiguous()          # (F_rank, K, T)
+    mark('dhtv')
     Y = y_local.transpose(-1, -2).contiguous()               # (F_rank, D, T)
     psd = get_power_spectral_density_matrix(Y, aligned)      # (F_rank, K, D, D)
+    mark('psd')
     K = psd.shape[1]
     total = psd.sum(1, keepdim=True)
     noise = (total - psd).contiguous()                       # interference + noise per target class
@@ -132,6 +159,8 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
                                   ).permute(1, 0, 2)
     else:
         raise ValueError(beamformer)
+    mark('beamformer')
     enhanced = apply_beamforming_vector(vectors.permute(1, 0, 2).contiguous(), Y.unsqueeze(0).expand(K, *Y.shape))
+    mark('apply')
     return dict(model=model, affiliation=aligned, mapping=mapping,
                 vectors=vectors, enhanced=enhanced.permute(1, 0, 2))
