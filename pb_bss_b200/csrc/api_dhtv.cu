@@ -2,6 +2,8 @@
 // DHTVPermutationAlignment.calculate_mapping (:295-355) with the 'cos' similarity
 // (_ScoreMatrix.multiply, :404-410) and the greedy assignment (:525-553), and
 // apply_mapping (:54-104).  See include/pbb.h.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "prof.cuh"
 
@@ -131,6 +133,150 @@ __global__ void __launch_bounds__(128) dhtv_assign_kernel(double* __restrict__ f
     for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
     for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
     *changed = 1;
+  }
+}
+
+// The whole alignment plan in ONE cooperative launch: every iteration is the same two phases as the launch pair above
+// (same arithmetic, same summation order: the mapping is bit-identical), separated by grid-wide barriers, and the
+// reference's early exit (:352-353) really skips the remaining iterations of a segment instead of launching kernels
+// that return at once.  plan: DEVICE copy of (iterations, start, end) triples.
+// Grid-wide barrier of a cooperative launch (all CTAs are resident): a monotonic arrival counter, one atomic and a
+// short acquire spin per CTA -- about a third of the latency of cooperative_groups' grid.sync() here.
+__device__ __forceinline__ void dhtv_grid_barrier(unsigned* counter, unsigned& generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++generation;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = generation * gridDim.x;
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ feat, double* __restrict__ partial,
+                                                        int* __restrict__ changed, const int* __restrict__ plan,
+                                                        int nplan, int K, int F, int T,
+                                                        long long* __restrict__ mapping, unsigned* __restrict__ bar) {
+  unsigned generation = 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* cent = reinterpret_cast<double*>(smem_raw);  // [K][T]
+  __shared__ double red[4];
+  __shared__ double cnorm[kDhtvMaxK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int gwarps = gridDim.x * 4, gwarp = blockIdx.x * 4 + warp;
+  int idx = 0;
+  for (int p = 0; p < nplan; ++p) {
+    const int iters = plan[3 * p], start = plan[3 * p + 1], end = plan[3 * p + 2];
+    const int n = end - start, per = (n + kDhtvSlices - 1) / kDhtvSlices;
+    for (int it = 0; it < iters; ++it, ++idx) {
+      // ---- phase A: partial[slice][k][t] = sum over the slice's bins (dhtv_centroid_kernel) ----
+      for (int e = gtid; e < kDhtvSlices * K * T; e += gthreads) {
+        const int sl = e / (K * T), i = e - sl * (K * T);
+        const int k = i / T, t = i - k * T;
+        const int f0 = start + sl * per, f1 = min(end, f0 + per);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int f = f0;
+        for (; f + 3 < f1; f += 4) {
+          s0 += feat[((size_t)k * F + f) * T + t];
+          s1 += feat[((size_t)k * F + f + 1) * T + t];
+          s2 += feat[((size_t)k * F + f + 2) * T + t];
+          s3 += feat[((size_t)k * F + f + 3) * T + t];
+        }
+        for (; f < f1; ++f) s0 += feat[((size_t)k * F + f) * T + t];
+        partial[(size_t)sl * K * T + i] = (s0 + s1) + (s2 + s3);
+      }
+      dhtv_grid_barrier(bar, generation);
+      // ---- phase B: one warp per bin (dhtv_assign_kernel); CTAs without a bin skip the centroid ----
+      if (blockIdx.x * 4 < n) {
+        const double inv_n = 1.0 / (double)n;
+#pragma unroll 4
+        for (int i = tid; i < K * T; i += blockDim.x) {
+          double v[kDhtvSlices];
+#pragma unroll
+          for (int sl = 0; sl < kDhtvSlices; ++sl) v[sl] = __ldcg(partial + (size_t)sl * K * T + i);
+          double s = 0.0;
+#pragma unroll
+          for (int sl = 0; sl < kDhtvSlices; ++sl) s += v[sl];
+          cent[i] = s * inv_n;
+        }
+        __syncthreads();
+        for (int k = 0; k < K; ++k) {
+          double s = 0.0;
+          for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
+          const double nn = sqrt(block_sum(s, red));
+          if (tid == 0) cnorm[k] = fmax(nn, kTiny);
+        }
+        __syncthreads();
+        for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
+        __syncthreads();
+        for (int f = start + gwarp; f < end; f += gwarps) {
+          // scores[kr][km] = <centroid kr, feature km of this bin>: the feature row is fetched 16 values per lane
+          // at a time with every load in flight (the plain loop is a chain of dependent L2 round trips); each
+          // (kr, km) sum still runs over t in ascending order, so the result is bit-identical to dhtv_assign_kernel
+          double score[kDhtvMaxK * kDhtvMaxK];
+          for (int i = 0; i < K * K; ++i) score[i] = 0.0;
+          for (int c0 = 0; c0 < T; c0 += 512) {
+            for (int km = 0; km < K; ++km) {
+              double v[16];
+              const double* __restrict__ row = feat + ((size_t)km * F + f) * T;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int t = c0 + lane + 32 * j;
+                v[j] = t < T ? __ldcg(row + t) : 0.0;
+              }
+              for (int kr = 0; kr < K; ++kr) {
+                double sacc = score[kr * K + km];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int t = c0 + lane + 32 * j;
+                  if (t < T) sacc += v[j] * cent[kr * T + t];
+                }
+                score[kr * K + km] = sacc;
+              }
+            }
+          }
+          for (int i = 0; i < K * K; ++i) score[i] = warp_sum(score[i]);
+          int perm[kDhtvMaxK];
+          for (int r = 0; r < K; ++r) {
+            int bi = 0, bj = 0;
+            double best = -INFINITY;
+            bool found = false;
+            for (int i = 0; i < K; ++i)
+              for (int j = 0; j < K; ++j) {
+                const double v = score[i * K + j];
+                if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
+              }
+            for (int j = 0; j < K; ++j) score[bi * K + j] = -INFINITY;
+            for (int i = 0; i < K; ++i) score[i * K + bj] = -INFINITY;
+            perm[bi] = bj;
+          }
+          bool ident = true;
+          for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
+          if (ident) continue;
+          for (int t = lane; t < T; t += 32) {
+            double v[kDhtvMaxK];
+            for (int k = 0; k < K; ++k) v[k] = feat[((size_t)k * F + f) * T + t];
+            for (int k = 0; k < K; ++k) feat[((size_t)k * F + f) * T + t] = v[perm[k]];
+          }
+          if (lane == 0) {
+            long long mv[kDhtvMaxK];
+            for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
+            for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
+            changed[idx] = 1;
+          }
+        }
+      }
+      dhtv_grid_barrier(bar, generation);
+      if (__ldcg(changed + idx) == 0) {  // nothing moved: the segment has converged (:352-353)
+        idx += iters - it;
+        break;
+      }
+    }
   }
 }
 
@@ -283,7 +429,7 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
   // centroid scratch: kDhtvSlices * K * T doubles of partial sums, then the int "changed" flags
   double* partial = centroid;
   int* changed = reinterpret_cast<int*>(centroid + (size_t)kDhtvSlices * K * T);
-  PBB_CUDA(cudaMemsetAsync(changed, 0, (size_t)(total_iters + 1) * sizeof(int), st));
+  PBB_CUDA(cudaMemsetAsync(changed, 0, (size_t)(total_iters + 2) * sizeof(int), st));
   PBB_CHECK_ARG((size_t)K * T * sizeof(double) <= 200 * 1024, 4, "K * T too large for the shared-memory centroid");
   PBB_CUDA(cudaFuncSetAttribute(dhtv_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   {
@@ -291,6 +437,30 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
     dhtv_normalize_kernel<<<K * F, 128, 0, st>>>(mask, features, K * F, T);
     dhtv_init_mapping_kernel<<<(K * F + 255) / 256, 256, 0, st>>>(mapping, K, F);
     PBB_CUDA(cudaGetLastError());
+  }
+  // One cooperative launch runs the whole plan (PBB_DHTV_MULTI=1: the launch pair per iteration, for A/B).
+  static const bool multi = getenv("PBB_DHTV_MULTI") != nullptr;
+  int dev = 0, coop = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  PBB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!multi && coop) {
+    // the plan travels in the scratch, behind the flags
+    int* plan_dev = changed + total_iters + 2;
+    unsigned* bar = reinterpret_cast<unsigned*>(changed + total_iters + 1);  // zeroed with the flags
+    PBB_CUDA(cudaMemcpyAsync(plan_dev, plan, (size_t)3 * nplan * sizeof(int), cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)K * T * sizeof(double);
+    PBB_CUDA(cudaFuncSetAttribute(dhtv_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 0, sms = 0;
+    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dhtv_coop_kernel, 128, smem));
+    PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = (kDhtvSlices * K * T + 127) / 128;  // one phase-A element per thread
+    if (grid > per_sm * sms) grid = per_sm * sms;
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&features, (void*)&partial, (void*)&changed, (void*)&plan_dev, (void*)&nplan,
+                    (void*)&K, (void*)&F, (void*)&T, (void*)&mapping, (void*)&bar};
+    LaunchScope ls("dhtv_coop_kernel", st);
+    PBB_CUDA(cudaLaunchCooperativeKernel((const void*)dhtv_coop_kernel, dim3(grid), dim3(128), args, smem, st));
+    return 0;
   }
   LaunchScope ls("dhtv_iterations", st);
   int idx = 0;
@@ -312,7 +482,8 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
 size_t pbb_dhtv_scratch_doubles(int K, int T, const int* plan, int nplan) {
   size_t iters = 0;
   for (int p = 0; p < nplan; ++p) iters += (size_t)plan[3 * p];
-  return (size_t)kDhtvSlices * K * T + (iters + 2) / 2 + 2;
+  // partial sums, the per-iteration "changed" flags, the device copy of the plan
+  return (size_t)kDhtvSlices * K * T + (iters + 3) / 2 + 2 + ((size_t)3 * nplan + 1) / 2 + 1;
 }
 
 int pbb_apply_mapping(const double* mask, const long long* mapping, int K, int F, int T, double* out,
