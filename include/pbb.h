@@ -280,6 +280,13 @@ size_t pbb_dhtv_scratch_doubles(int K, int T, const int* plan, int nplan);
 int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan,
                      int nplan, double* features, double* centroid,
                      long long* mapping, void* stream);
+/* The same with the reference's options (permutation_alignment.py:133-163): metric 0 = 'multiply' (raw masks, inner
+ * product), 1 = 'cos' (the default: features and centroid L2-normalised over time), 2 = 'euclidean' (minus the
+ * distance); algorithm 0 = 'greedy', 1 = 'optimal' (brute force over the K! permutations).  The whole plan runs in
+ * one cooperative launch (grid-wide barriers between the centroid and the assignment phase of every iteration). */
+int pbb_dhtv_mapping_ex(const double* mask, int K, int F, int T, const int* plan,
+                        int nplan, double* features, double* centroid,
+                        long long* mapping, int metric, int algorithm, void* stream);
 
 /* apply_mapping (:54-104): out[k, f, :] = mask[mapping[k, f], f, :]. */
 int pbb_apply_mapping(const double* mask, const long long* mapping, int K,

@@ -89,6 +89,12 @@ def make_cacgmm_coupled(ref):
     init = synth.init_affiliation(65, 2, 60, seed=5)
     _cacgmm_case(ref, 'cacgmm_tied_time', y, init, 5, weight_constant_axis=(-3,))
     _cacgmm_case(ref, 'cacgmm_tied', y, init, 5, weight_constant_axis=(-3, -1))
+    # saliency together with tied weights, and tied weights with a batch dim in front of the bins
+    sal = np.random.RandomState(9).uniform(0.2, 1.0, size=(65, 60))
+    _cacgmm_case(ref, 'cacgmm_tied_time_saliency', y, init, 4, weight_constant_axis=(-3,), saliency=sal)
+    _cacgmm_case(ref, 'cacgmm_tied_saliency', y, init, 4, weight_constant_axis=(-3, -1), saliency=sal)
+    yb = np.stack([y[:33], synth.structured_stft(33, 60, 4, 2, seed=22)[0]])
+    _cacgmm_case(ref, 'cacgmm_tied_batch', yb, np.stack([init[:33], init[32:]]), 4, weight_constant_axis=(-3,))
     al = pa.DHTVPermutationAlignment(stft_size=128, segment_start=20, segment_width=20, segment_shift=5,
                                      main_iterations=5, sub_iterations=2)
     T = ref.distribution.CACGMMTrainer
@@ -174,6 +180,11 @@ def make_cwmm_coupled(ref):
         if inline:
             out['plan'] = np.asarray(al.alignment_plan)
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    sal = np.random.RandomState(9).uniform(0.2, 1.0, size=(F, N))
+    model = T().fit(y, initialization=init, iterations=4, weight_constant_axis=(-3,), saliency=sal)
+    np.savez_compressed(os.path.join(OUT, 'cwmm_tied_time_saliency.npz'), y=y, init=init, iterations=4, saliency=sal,
+                        weight=model.weight, mode=model.complex_watson.mode,
+                        concentration=model.complex_watson.concentration, affiliation=model.predict(y))
 
 
 def make_permutation(ref):
@@ -204,6 +215,14 @@ def make_permutation(ref):
     out['c_mask'] = mask
     out['c_plan'] = np.asarray(al.alignment_plan)
     out['c_mapping'] = al.calculate_mapping(mask.copy())
+    # the non-default options of DHTV (:133-163) on mask (a): every metric with both assignments
+    mask = out['a_mask']
+    for metric in ('cos', 'multiply', 'euclidean'):
+        for algorithm in ('greedy', 'optimal'):
+            al = pa.DHTVPermutationAlignment(
+                stft_size=512, segment_start=70, segment_width=100, segment_shift=20, main_iterations=20,
+                sub_iterations=2, similarity_metric=metric, algorithm=algorithm)
+            out[f'opt_{metric}_{algorithm}'] = al.calculate_mapping(mask.copy())
     # greedy assignment known answer, permutation_alignment.py:475-508
     sm = np.array([[11, 10, 0], [4, 5, 10], [6, 0, 5]])
     out['score'] = sm
@@ -311,12 +330,45 @@ def make_full_size(ref):
         affiliation_8=aff[..., ::8])
 
 
+def make_initializer(ref):
+    """pb_bss.initializer: iid draws after np.random.seed(0), flag, deflationSeed (deflation.py:6-89)."""
+    import pb_bss.initializer as RI
+    out = {}
+    Y = np.ones([4, 5, 3])
+    for name in ('uniform_normalized', 'dirichlet_uniform', 'one_hot'):
+        for pf in (False, True):
+            np.random.seed(0)
+            out[f'{name}_{int(pf)}'] = np.array(getattr(RI.iid, name)(Y, 2, permutation_free=pf))
+    np.random.seed(0)
+    out['dirichlet_a3'] = np.array(RI.iid.dirichlet(np.ones([2, 7, 3]), 3, alpha=3))
+    out['flag_2'] = np.array(RI.deterministic.flag(Y, 2, permutation_free=True))
+    out['flag_4_min'] = np.array(RI.deterministic.flag(np.ones([1, 5, 3]), 4, minimum=0.1, permutation_free=True))
+    y = synth.structured_stft(257, 60, 4, 3, seed=17)[0]
+    out['deflation_y'] = y
+    out['deflation_pf'] = RI.deflation.deflationSeed(y, 3, permutation_free=True)
+    out['deflation_nopf'] = RI.deflation.deflationSeed(y, 3, permutation_free=False, neighbors=3)
+    sal = np.random.RandomState(2).uniform(0.1, 1, size=(257, 60))
+    out['deflation_sal'] = sal
+    out['deflation_with_sal'] = RI.deflation.deflationSeed(y, 2, saliencies=sal, eps=1e-3)
+    np.savez_compressed(os.path.join(OUT, 'initializer.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == 'full':
         make_full_size(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'initializer':
+        make_initializer(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'permutation':
+        make_permutation(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'coupled':
+        make_cacgmm_coupled(ref)
+        make_cwmm_coupled(ref)
         return
     make_cacgmm(ref)
     make_cacgmm_coupled(ref)
@@ -327,6 +379,7 @@ def main():
     make_permutation_greedy_oracle(ref)
     make_beamformer(ref)
     make_bf_wrapper(ref)
+    make_initializer(ref)
     make_full_size(ref)
     total = 0
     for n in sorted(os.listdir(OUT)):

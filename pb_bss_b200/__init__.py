@@ -12,5 +12,6 @@ from . import _lib  # noqa: F401  (import must not need a GPU)
 from . import distribution  # noqa: F401
 from . import extraction  # noqa: F401
 from . import permutation_alignment  # noqa: F401
+from . import initializer  # noqa: F401
 
-__all__ = ['distribution', 'extraction', 'permutation_alignment']
+__all__ = ['distribution', 'extraction', 'permutation_alignment', 'initializer']

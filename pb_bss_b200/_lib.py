@@ -66,6 +66,7 @@ SIGNATURES = {
     'pbb_blind_analytic_normalization': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_dhtv_scratch_doubles': (_sz, [_i, _i, ctypes.POINTER(_i), _i]),
     'pbb_dhtv_mapping': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
+    'pbb_dhtv_mapping_ex': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i, _i, _vp]),
     'pbb_apply_mapping': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     'pbb_score_matrix': (_i, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, _i, _i, _i, _i, _vp, _vp]),
     'pbb_mapping_from_score_matrix': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -894,17 +894,9 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
   u.part = ws.part; u.weight_mode = weight_mode;
   u.spline.t = spline_t; u.spline.c = spline_c; u.spline.n = spline_n;
   u.spline.max_concentration = max_concentration;
-  // domain of the interpolant: first and last knot (repeated k + 1 times)
-  // are read on the host side of the ABI by the caller; here they are fetched lazily on the device
+  // (the domain of the interpolant -- first and last knot -- is read from the table on the device)
   u.mode = reinterpret_cast<double2*>(mode); u.concentration = concentration; u.weight = weight;
   u.coef = ws.coef; u.ld = ws.ld; u.ew = ws.ew; u.status = status;
-  {
-    double ends[2];
-    PBB_CUDA(cudaMemcpyAsync(&ends[0], spline_t, sizeof(double), cudaMemcpyDeviceToHost, st));
-    PBB_CUDA(cudaMemcpyAsync(&ends[1], spline_t + spline_n + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
-    PBB_CUDA(cudaStreamSynchronize(st));
-    u.spline.x_lo = ends[0]; u.spline.x_hi = ends[1];
-  }
   if (persistent) {
     // every EM iteration in one launch (em_persistent.cuh, MODEL = 1); the last iteration's raw
     // scatter sums go through cw_update_kernel for the reference-exact mode / concentration / weight
@@ -918,6 +910,17 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status; p.phase = ws.phase;
     p.spline = u.spline;
     if ((r = launch_persist_cw(p, D, K, dtype, st))) return r;
+#ifdef PBB_PHASE_TIMING
+    {
+      unsigned long long ph[16];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(ph, ws.phase, sizeof(ph), cudaMemcpyDeviceToHost);
+      unsigned long long tot = 0;
+      for (int i = 0; i < 8; ++i) tot += ph[i];
+      static const char* nm[8] = {"flag wait", "chunk top / staging", "tma-wait", "em-steps", "reduce", "update (jacobi)", "publish", "task-start"};
+      for (int i = 0; i < 8; ++i) fprintf(stderr, "[phase cw] %-20s %6.2f%%  %8.0f cycles per task\n", nm[i], 100.0 * ph[i] / (double)tot, ph[i] / (double)((size_t)F * iterations));
+    }
+#endif
     u.nch = 1;
     return launch_cw_update(u, st);
   }

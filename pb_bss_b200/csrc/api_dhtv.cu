@@ -140,6 +140,47 @@ __global__ void __launch_bounds__(128) dhtv_assign_kernel(double* __restrict__ f
 // (same arithmetic, same summation order: the mapping is bit-identical), separated by grid-wide barriers, and the
 // reference's early exit (:352-353) really skips the remaining iterations of a segment instead of launching kernels
 // that return at once.  plan: DEVICE copy of (iterations, start, end) triples.
+// Reverse permutation of one bin from its score matrix (_mapping_from_score_matrix, :458-590; every lane of the warp
+// computes the same).  greedy: K times the first maximum of the row-major flattened matrix, then blank its row and
+// column; optimal: the first best of itertools.permutations(range(K)) (lexicographic order, strict >), scores summed
+// left to right like Python's sum().
+__device__ __forceinline__ void dhtv_assign(double* __restrict__ score, int K, int optimal, int* __restrict__ perm) {
+  if (!optimal) {
+    for (int r = 0; r < K; ++r) {
+      int bi = 0, bj = 0;
+      double best = -INFINITY;
+      bool found = false;
+      for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+          const double v = score[i * K + j];
+          if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
+        }
+      for (int j = 0; j < K; ++j) score[bi * K + j] = -INFINITY;
+      for (int i = 0; i < K; ++i) score[i * K + bj] = -INFINITY;
+      perm[bi] = bj;
+    }
+    return;
+  }
+  int cand[kDhtvMaxK];
+  for (int k = 0; k < K; ++k) { cand[k] = k; perm[k] = k; }
+  double best = -INFINITY;
+  while (true) {
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += score[k * K + cand[k]];
+    if (sum > best) {
+      best = sum;
+      for (int k = 0; k < K; ++k) perm[k] = cand[k];
+    }
+    int i = K - 2;  // next lexicographic permutation
+    while (i >= 0 && cand[i] > cand[i + 1]) --i;
+    if (i < 0) break;
+    int j = K - 1;
+    while (cand[j] < cand[i]) --j;
+    { const int t = cand[i]; cand[i] = cand[j]; cand[j] = t; }
+    for (int a = i + 1, b = K - 1; a < b; ++a, --b) { const int t = cand[a]; cand[a] = cand[b]; cand[b] = t; }
+  }
+}
+
 // Grid-wide barrier of a cooperative launch (all CTAs are resident): a monotonic arrival counter, one atomic and a
 // short acquire spin per CTA -- about a third of the latency of cooperative_groups' grid.sync() here.
 __device__ __forceinline__ void dhtv_grid_barrier(unsigned* counter, unsigned& generation) {
@@ -160,7 +201,10 @@ __device__ __forceinline__ void dhtv_grid_barrier(unsigned* counter, unsigned& g
 __global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ feat, double* __restrict__ partial,
                                                         int* __restrict__ changed, const int* __restrict__ plan,
                                                         int nplan, int K, int F, int T,
-                                                        long long* __restrict__ mapping, unsigned* __restrict__ bar) {
+                                                        long long* __restrict__ mapping, unsigned* __restrict__ bar,
+                                                        int metric, int optimal) {
+  // metric: 1 = cos (features and centroid L2-normalised over time, score = inner product), 0 = multiply (inner
+  // product of the raw masks), 2 = euclidean (score = -distance), permutation_alignment.py:309-340,380-420
   unsigned generation = 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* cent = reinterpret_cast<double*>(smem_raw);  // [K][T]
@@ -205,15 +249,17 @@ __global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ fea
           cent[i] = s * inv_n;
         }
         __syncthreads();
-        for (int k = 0; k < K; ++k) {
-          double s = 0.0;
-          for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
-          const double nn = sqrt(block_sum(s, red));
-          if (tid == 0) cnorm[k] = fmax(nn, kTiny);
+        if (metric == 1) {
+          for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
+            const double nn = sqrt(block_sum(s, red));
+            if (tid == 0) cnorm[k] = fmax(nn, kTiny);
+          }
+          __syncthreads();
+          for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
+          __syncthreads();
         }
-        __syncthreads();
-        for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
-        __syncthreads();
         for (int f = start + gwarp; f < end; f += gwarps) {
           // scores[kr][km] = <centroid kr, feature km of this bin>: the feature row is fetched 16 values per lane
           // at a time with every load in flight (the plain loop is a chain of dependent L2 round trips); each
@@ -234,27 +280,21 @@ __global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ fea
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int t = c0 + lane + 32 * j;
-                  if (t < T) sacc += v[j] * cent[kr * T + t];
+                  if (t < T) {
+                    if (metric == 2) { const double dlt = v[j] - cent[kr * T + t]; sacc += dlt * dlt; }
+                    else sacc += v[j] * cent[kr * T + t];
+                  }
                 }
                 score[kr * K + km] = sacc;
               }
             }
           }
-          for (int i = 0; i < K * K; ++i) score[i] = warp_sum(score[i]);
-          int perm[kDhtvMaxK];
-          for (int r = 0; r < K; ++r) {
-            int bi = 0, bj = 0;
-            double best = -INFINITY;
-            bool found = false;
-            for (int i = 0; i < K; ++i)
-              for (int j = 0; j < K; ++j) {
-                const double v = score[i * K + j];
-                if (!found || v > best) { best = v; bi = i; bj = j; found = true; }
-              }
-            for (int j = 0; j < K; ++j) score[bi * K + j] = -INFINITY;
-            for (int i = 0; i < K; ++i) score[i * K + bj] = -INFINITY;
-            perm[bi] = bj;
+          for (int i = 0; i < K * K; ++i) {
+            score[i] = warp_sum(score[i]);
+            if (metric == 2) score[i] = -sqrt(score[i]);  // the minus turns the distance into a similarity (:412-418)
           }
+          int perm[kDhtvMaxK];
+          dhtv_assign(score, K, optimal, perm);
           bool ident = true;
           for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
           if (ident) continue;
@@ -412,7 +452,14 @@ extern "C" {
 
 int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, int nplan, double* features,
                      double* centroid, long long* mapping, void* stream) {
+  return pbb_dhtv_mapping_ex(mask, K, F, T, plan, nplan, features, centroid, mapping, 1, 0, stream);
+}
+
+int pbb_dhtv_mapping_ex(const double* mask, int K, int F, int T, const int* plan, int nplan, double* features,
+                        double* centroid, long long* mapping, int metric, int algorithm, void* stream) {
   PBB_CHECK_ARG(mask != nullptr, 1, "mask is null");
+  PBB_CHECK_ARG(metric >= 0 && metric <= 2, 10, "metric: 0 multiply, 1 cos, 2 euclidean");
+  PBB_CHECK_ARG(algorithm == 0 || algorithm == 1, 11, "algorithm: 0 greedy, 1 optimal");
   PBB_CHECK_ARG(K > 0 && K <= kDhtvMaxK, 2, "need 0 < K < 10 (permutation_alignment.py:200)");
   PBB_CHECK_ARG(F > 0, 3, "F must be positive");
   PBB_CHECK_ARG(T > 0, 4, "T must be positive");
@@ -434,7 +481,8 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
   PBB_CUDA(cudaFuncSetAttribute(dhtv_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   {
     LaunchScope ls("dhtv_normalize_kernel", st);
-    dhtv_normalize_kernel<<<K * F, 128, 0, st>>>(mask, features, K * F, T);
+    if (metric == 1) dhtv_normalize_kernel<<<K * F, 128, 0, st>>>(mask, features, K * F, T);
+    else PBB_CUDA(cudaMemcpyAsync(features, mask, (size_t)K * F * T * sizeof(double), cudaMemcpyDeviceToDevice, st));
     dhtv_init_mapping_kernel<<<(K * F + 255) / 256, 256, 0, st>>>(mapping, K, F);
     PBB_CUDA(cudaGetLastError());
   }
@@ -457,11 +505,13 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan, i
     if (grid > per_sm * sms) grid = per_sm * sms;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&features, (void*)&partial, (void*)&changed, (void*)&plan_dev, (void*)&nplan,
-                    (void*)&K, (void*)&F, (void*)&T, (void*)&mapping, (void*)&bar};
+                    (void*)&K, (void*)&F, (void*)&T, (void*)&mapping, (void*)&bar, (void*)&metric, (void*)&algorithm};
     LaunchScope ls("dhtv_coop_kernel", st);
     PBB_CUDA(cudaLaunchCooperativeKernel((const void*)dhtv_coop_kernel, dim3(grid), dim3(128), args, smem, st));
     return 0;
   }
+  PBB_CHECK_ARG(metric == 1 && algorithm == 0, 10,
+                "only similarity_metric='cos' with algorithm='greedy' has the multi-launch path (no cooperative launch here)");
   LaunchScope ls("dhtv_iterations", st);
   int idx = 0;
   for (int p = 0; p < nplan; ++p) {

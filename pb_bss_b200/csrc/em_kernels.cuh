@@ -669,8 +669,9 @@ struct CwSpline {
 
 __device__ inline double cw_spline_eval(const CwSpline& sp, double x) {
   if (!(x == x)) return x;                      // NaN in, NaN out
-  if (x < sp.x_lo) return 0.0;                  // fill_value = (0, max_concentration)
-  if (x > sp.x_hi) return sp.max_concentration;
+  // domain of the interpolant = first / last knot, read from the table (no host round trip)
+  if (x < __ldg(sp.t)) return 0.0;               // fill_value = (0, max_concentration)
+  if (x > __ldg(sp.t + sp.n + 2)) return sp.max_concentration;
   const int k = 2, n = sp.n;
   int lo = k, hi = n;  // find i in [k, n-1] with t[i] <= x < t[i+1]
   while (hi - lo > 1) {

@@ -41,13 +41,13 @@ def _weight_mode(weight_constant_axis, ndim):
         axes = tuple(sorted(a % ndim - ndim for a in weight_constant_axis))
     if axes == (-1,):
         return _lib.WEIGHT_TIME
-    if ndim == 3 and axes == (-3,):
+    if ndim >= 3 and axes == (-3,):
         return _lib.WEIGHT_TIED_TIME
-    if ndim == 3 and axes == (-3, -1):
+    if ndim >= 3 and axes == (-3, -1):
         return _lib.WEIGHT_TIED
     raise NotImplementedError(
         f'weight_constant_axis={weight_constant_axis!r}: supported on the '
-        'device are (-1,), -2 and, for (F, K, T) affiliations, (-3,) / (-3, -1).')
+        'device are (-1,), -2, (-3,) and (-3, -1) (the last independent dim, the bins, tied).')
 
 
 def _flatten_obs(y):
@@ -226,6 +226,14 @@ class CACGMMTrainer:
             raise TypeError('No sufficient initialization.')
         assert K < 20, f'num_classes: {K}, sure?'
         weight_mode = _weight_mode(weight_constant_axis, len(independent) + 2)
+        if weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED) and len(independent) > 1:
+            # the weights are tied over the LAST independent dim (the bins); the dims in front of it stay
+            # independent problems: fit them one after the other and stack the models
+            return self._fit_tied_leading(
+                y, initialization, independent, iterations, like_numpy, saliency=saliency,
+                source_activity_mask=source_activity_mask, weight_constant_axis=weight_constant_axis,
+                hermitize=hermitize, covariance_norm=covariance_norm, affiliation_eps=affiliation_eps,
+                eigenvalue_floor=eigenvalue_floor, inline_permutation_aligner=inline_permutation_aligner)
         if inline_permutation_aligner is not None or weight_mode in (_lib.WEIGHT_TIED_TIME, _lib.WEIGHT_TIED):
             # frequency-tied weights and the inline permutation alignment couple the bins inside the
             # EM loop (cacgmm.py:252-278): one E-step / alignment / M-step round trip per iteration
@@ -293,6 +301,33 @@ class CACGMMTrainer:
                 covariance_eigenvalues=_device.to_host(
                     lam.reshape(*independent, K, D), like_numpy)))
 
+    def _fit_tied_leading(self, y, initialization, independent, iterations, like_numpy, *, saliency,
+                          source_activity_mask, **kw):
+        """Frequency-tied weights with more than one independent dim, e.g. (B, F, T, D): every index of the leading
+        dims is its own coupled fit (the reference's mean over axis -3 keeps them apart, mixture_model_utils.py:187)."""
+        lead = tuple(independent[:-1])
+
+        def pick(x, idx):
+            if x is None or isinstance(x, CACGMM):
+                return x
+            nlead = x.ndim - (y.ndim - len(lead))     # how many of the leading dims x carries
+            if nlead <= 0:
+                return x
+            sub = tuple(i if x.shape[d] != 1 else 0 for d, i in enumerate(idx[len(lead) - nlead:]))
+            return x[sub]
+
+        assert not isinstance(initialization, CACGMM), 'warm start with tied weights: one leading dim only'
+        models = [self.fit(pick(y, idx), initialization=pick(initialization, idx), iterations=iterations,
+                           saliency=pick(saliency, idx), source_activity_mask=pick(source_activity_mask, idx), **kw)
+                  for idx in np.ndindex(*lead)]
+        stack = (lambda xs: np.stack(xs).reshape(*lead, *xs[0].shape)) if like_numpy else \
+            (lambda xs: torch.stack(xs).reshape(*lead, *xs[0].shape))
+        return CACGMM(
+            weight=stack([m.weight for m in models]),
+            cacg=ComplexAngularCentralGaussian(
+                covariance_eigenvectors=stack([m.cacg.covariance_eigenvectors for m in models]),
+                covariance_eigenvalues=stack([m.cacg.covariance_eigenvalues for m in models])))
+
     def _fit_coupled(self, yd, like_numpy, init_dev, model_in, K, iterations, saliency, source_activity_mask,
                      weight_mode, hermitize, covariance_norm, affiliation_eps, eigenvalue_floor, aligner,
                      weight_constant_axis, total_bins=None, bin_group=None):
@@ -313,8 +348,13 @@ class CACGMMTrainer:
                        f'require `affiliation.ndim == 3` and a corresponding `weight_constant_axis` '
                        f'({weight_constant_axis}).')
             assert len(independent) == 1 and tied, message
+        sal_w = None
         if tied and saliency is not None:
-            raise NotImplementedError('saliency together with frequency-tied weights is not on the device yet')
+            # estimate_mixture_weight with a saliency (mixture_model_utils.py:192-203): the tied weight is the
+            # L1-normalised sum of affiliation * saliency over the bins (and frames)
+            if F_all != F:
+                raise NotImplementedError('saliency with frequency-tied weights is single-rank only')
+            sal_w = _device.to_device(saliency, torch.float64).expand(*independent, N).reshape(F, 1, N)
         lib = _lib.load()
         model = model_in
         affiliation = init_dev.reshape(*independent, K, N) if init_dev is not None else None
@@ -339,11 +379,15 @@ class CACGMMTrainer:
                 covariance_norm=covariance_norm, eigenvalue_floor=eigenvalue_floor,
                 weight_constant_axis=m_axis)
             if tied:
-                aff = affiliation.reshape(F, K, N).contiguous()
+                aff = affiliation.reshape(F, K, N)
+                if sal_w is not None:
+                    aff = aff * sal_w
+                aff = aff.contiguous()
                 w_kt = _device.empty((K, N), torch.float64)
                 w_k = _device.empty((K,), torch.float64)
+                flags = int(weight_mode == _lib.WEIGHT_TIED) | (2 if sal_w is not None else 0)
                 _lib.check(lib.pbb_mixture_weight_over_bins(
-                    _device.ptr(aff), F, K, N, int(weight_mode == _lib.WEIGHT_TIED), _device.ptr(w_kt),
+                    _device.ptr(aff), F, K, N, flags, _device.ptr(w_kt),
                     _device.ptr(w_k), _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
                 if F_all != F:  # sum over the other ranks' bins
                     w_kt = parallel.mean_over_all_bins(w_kt, F, F_all, bin_group)

@@ -160,8 +160,6 @@ class CWMMTrainer:
                        f'require `affiliation.ndim == 3` and a corresponding `weight_constant_axis` '
                        f'({weight_constant_axis}).')
             assert len(independent) == 1 and tied, message
-        if tied and sal is not None:
-            raise NotImplementedError('saliency together with frequency-tied weights is not on the device yet')
         lib = _lib.load()
         affiliation = init
         model = None
@@ -179,8 +177,10 @@ class CWMMTrainer:
                 w_kt = _device.empty((K, N), torch.float64)
                 w_k = _device.empty((K,), torch.float64)
                 flags = (1 if weight_mode == _lib.WEIGHT_TIED else 0) | 2
+                # with a saliency the tied weight sums affiliation * saliency (mixture_model_utils.py:192-203)
+                aff_w = (affiliation * sal[:, None, :] if sal is not None else affiliation).contiguous()
                 _lib.check(lib.pbb_mixture_weight_over_bins(
-                    _device.ptr(affiliation.contiguous()), F, K, N, flags, _device.ptr(w_kt), _device.ptr(w_k),
+                    _device.ptr(aff_w), F, K, N, flags, _device.ptr(w_kt), _device.ptr(w_k),
                     _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
                 model.weight = w_kt[None] if weight_mode == _lib.WEIGHT_TIED_TIME else w_k[None, :, None]
         if like_numpy:

@@ -81,10 +81,8 @@ class DHTVPermutationAlignment(_PermutationAlignment):
         self.sub_iterations = sub_iterations
         self.similarity_metric = similarity_metric
         self.algorithm = algorithm
-        if similarity_metric != 'cos' or algorithm != 'greedy':
-            raise NotImplementedError(
-                "only similarity_metric='cos' with algorithm='greedy' (the "
-                'defaults of the reference) run on the device')
+        # like the reference (:157-162) an unknown metric fails here, an unknown algorithm when it is first used
+        self._metric = _metric_code(similarity_metric)
 
     @classmethod
     def from_stft_size(cls, stft_size, similarity_metric='cos'):
@@ -142,9 +140,12 @@ class DHTVPermutationAlignment(_PermutationAlignment):
         feat = _device.empty((K, F, T), torch.float64)
         cent = _device.empty((int(lib.pbb_dhtv_scratch_doubles(K, T, plan_p, int(plan.shape[0]))),), torch.float64)
         mapping = _device.empty((K, F), torch.int64)
-        _lib.check(lib.pbb_dhtv_mapping(_device.ptr(m), K, F, T, plan_p, int(plan.shape[0]),
-                                        _device.ptr(feat), _device.ptr(cent), _device.ptr(mapping),
-                                        _device.stream_ptr()), 'pbb_dhtv_mapping')
+        if self.algorithm not in _ALGORITHMS:
+            raise ValueError(self.algorithm)   # _mapping_from_score_matrix (:588-589)
+        _lib.check(lib.pbb_dhtv_mapping_ex(_device.ptr(m), K, F, T, plan_p, int(plan.shape[0]),
+                                           _device.ptr(feat), _device.ptr(cent), _device.ptr(mapping),
+                                           self._metric, _ALGORITHMS[self.algorithm],
+                                           _device.stream_ptr()), 'pbb_dhtv_mapping_ex')
         return _device.to_host(mapping, like_numpy)
 
 

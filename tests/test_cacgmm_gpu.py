@@ -308,6 +308,31 @@ def test_frequency_tied_weights_match_reference_golden(name, axis):
     np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize('name,axis', [('cacgmm_tied_time_saliency', (-3,)), ('cacgmm_tied_saliency', (-3, -1))])
+def test_tied_weights_with_saliency_match_reference_golden(name, axis):
+    """estimate_mixture_weight with a saliency (mixture_model_utils.py:192-203) and frequency-tied weights."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    g = load_golden(name)
+    model = CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=int(g['iterations']),
+                                weight_constant_axis=axis, saliency=g['kw_saliency'])
+    assert model.weight.shape == g['weight'].shape
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), g['covariance'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-6, atol=1e-9)
+
+
+def test_tied_weights_with_a_batch_dim_match_reference_golden():
+    """(B, F, T, D) with weight_constant_axis=(-3,): the weights are tied over the bins of every batch element
+    separately (mean over axis -3, keepdims), the reference's shape (B, 1, K, T)."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    g = load_golden('cacgmm_tied_batch')
+    model = CACGMMTrainer().fit(g['y'], initialization=g['init'], iterations=int(g['iterations']),
+                                weight_constant_axis=(-3,))
+    assert model.weight.shape == g['weight'].shape, (model.weight.shape, g['weight'].shape)
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(_cov(model), g['covariance'], rtol=1e-6, atol=1e-9)
+
+
 def test_inline_permutation_alignment_matches_reference_golden():
     """inline_permutation_aligner (cacgmm.py:260-267, mixture_model_utils.py:264-306)."""
     from pb_bss_b200.distribution import CACGMMTrainer

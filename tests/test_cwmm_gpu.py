@@ -77,6 +77,18 @@ def test_spline_table_reproduces_reference_inverse(D):
     np.testing.assert_allclose(tr.hypergeometric_ratio_inverse(lam), g['kappa'], rtol=1e-12)
 
 
+def test_tied_weights_with_saliency_match_reference_golden():
+    from pb_bss_b200.distribution import CWMMTrainer
+    g = load_golden('cwmm_tied_time_saliency')
+    model = CWMMTrainer().fit(g['y'], initialization=g['init'], iterations=int(g['iterations']),
+                              weight_constant_axis=(-3,), saliency=g['saliency'])
+    assert model.weight.shape == g['weight'].shape
+    np.testing.assert_allclose(model.weight, g['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.complex_watson.concentration, g['concentration'], rtol=1e-6)
+    np.testing.assert_allclose(cos_similarity(model.complex_watson.mode, g['mode']), 1, atol=1e-9)
+    np.testing.assert_allclose(model.predict(g['y']), g['affiliation'], rtol=1e-5, atol=1e-8)
+
+
 def test_full_size_config4_properties():
     """BASELINE.json config 4 (F=257, T=1000, D=6, K=4, 50 iterations)."""
     from pb_bss_b200.distribution import CWMMTrainer

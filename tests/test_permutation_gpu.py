@@ -27,6 +27,26 @@ def test_mapping_matches_reference_golden():
     np.testing.assert_array_equal(al.calculate_mapping(g['c_mask']), g['c_mapping'])
 
 
+@pytest.mark.parametrize('metric', ['cos', 'multiply', 'euclidean'])
+@pytest.mark.parametrize('algorithm', ['greedy', 'optimal'])
+def test_dhtv_options_match_reference_golden(metric, algorithm):
+    """similarity_metric / algorithm of DHTVPermutationAlignment (permutation_alignment.py:133-163,380-420,556-585)."""
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+    g = load_golden('permutation')
+    al = DHTVPermutationAlignment(stft_size=512, segment_start=70, segment_width=100, segment_shift=20,
+                                  main_iterations=20, sub_iterations=2, similarity_metric=metric, algorithm=algorithm)
+    np.testing.assert_array_equal(al.calculate_mapping(g['a_mask']), g[f'opt_{metric}_{algorithm}'])
+
+
+def test_dhtv_option_errors():
+    from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+    kw = dict(stft_size=512, segment_start=70, segment_width=100, segment_shift=20, main_iterations=2, sub_iterations=2)
+    with pytest.raises(AttributeError):
+        DHTVPermutationAlignment(similarity_metric='coss', **kw)
+    with pytest.raises(ValueError):
+        DHTVPermutationAlignment(algorithm='best', **kw).calculate_mapping(load_golden('permutation')['a_mask'])
+
+
 def test_full_size_alignment_recovers_a_random_permutation():
     """K=3, F=513, T=500 (BASELINE.json config 3): permute a consistent mask per
     bin, align, and check against the oracle and the sortedness property
