@@ -165,6 +165,51 @@ int pbb_mixture_weight_over_bins(const double* affiliation, int F, int K, int T,
                                  double* weight_k, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Integrated spatial + spectral model (pb_bss/distribution/gcacgmm.py): cACG of the observation combined with a
+ * Gaussian over per-(bin, frame) embeddings (F, T, E).  The spatial part reuses pbb_cacgmm_predict (quadratic form)
+ * and pbb_cacgmm_mstep; these entries are the pieces around them.
+ * ------------------------------------------------------------------------ */
+
+/* ComplexAngularCentralGaussian._log_pdf (cacg.py:198-201) from the quadratic form: log_pdf = -D log max(|q|, tiny)
+ * - sum_d log eigenvalues.  quadratic, log_pdf (F, K, T); eigenvalues (F, K, D). */
+int pbb_cacg_log_pdf(const double* quadratic, const double* eigenvalues, int F, int K,
+                     int T, int D, double* log_pdf, void* stream);
+
+/* DiagonalGaussian / SphericalGaussian.log_pdf (gaussian.py:57-135) of every embedding under every class:
+ * embedding (F, T, E), mean / precision_cholesky (K, E) (spherical: the scalar repeated E times), log_det (K)
+ * -> log_pdf (F, K, T).  E <= 64.  diagonal != 0 evaluates the reference's DiagonalGaussian expression, whose einsum
+ * '...dD,...nD->...nd' (gaussian.py:79-87) contracts precision_cholesky[d][:] of EVERY class d with the centred
+ * observation and sums the squares over d -- reproduced as is, because the model is a drop-in. */
+int pbb_gaussian_log_pdf(const double* embedding, const double* mean,
+                         const double* precision_cholesky, const double* log_det,
+                         int F, int T, int E, int K, int diagonal, double* log_pdf,
+                         void* stream);
+
+/* GaussianTrainer._fit (gaussian.py:155-193) over the F*T embeddings with weights weight (F, K, T): mean (K, E),
+ * covariance (K, E) ('diagonal') or (K) ('spherical'); two passes (mean, then centred second moments), fixed
+ * summation order.  scratch: pbb_gaussian_fit_scratch_doubles doubles. */
+size_t pbb_gaussian_fit_scratch_doubles(int F, int E, int K);
+int pbb_gaussian_fit(const double* embedding, const double* weight, int F, int T, int E,
+                     int K, int spherical, double* mean, double* covariance,
+                     double* scratch, void* stream);
+
+/* log_pdf_to_affiliation (mixture_model_utils.py:7-55) of scale_a * log_pdf_a + scale_b * log_pdf_b (log_pdf_b may be
+ * null) with the weight layouts of pbb_cacgmm_predict; inline_pa != 0:
+ * log_pdf_to_affiliation_for_integration_models_with_inline_pa (:58-130) -- per bin the classes of log_pdf_a are
+ * re-paired with those of log_pdf_b by the first permutation (itertools order) that maximises the auxiliary function;
+ * permutation (F, K) int32 (may be null) receives the choice.  K <= 6. */
+int pbb_log_pdf_to_affiliation(const double* log_pdf_a, const double* log_pdf_b,
+                               double scale_a, double scale_b, const double* weight,
+                               int weight_mode, const uint8_t* activity,
+                               double affiliation_eps, int inline_pa, int F, int K, int T,
+                               double* affiliation, int* permutation, void* stream);
+
+/* Per-bin class weights of the integrated models (gcacgmm.py:286-291, weight_constant_axis (-1,)):
+ * weight[f][k] = sum_t m[f][k][t] / sum_k sum_t m[f][k][t]. */
+int pbb_class_weight(const double* masked_affiliation, int F, int K, int T, double* weight,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
  * Complex Watson mixture model (pb_bss/distribution/cwmm.py, complex_watson.py).
  *
  * Device model: mode (F, K, D) complex128, concentration (F, K), weight (F, K)

@@ -330,6 +330,35 @@ def make_full_size(ref):
         affiliation_8=aff[..., ::8])
 
 
+def make_gcacgmm(ref):
+    """Integrated model GCACGMM (gcacgmm.py:38-333): spherical / diagonal Gaussians over embeddings, weight layouts,
+    the inline pairing of spatial and spectral classes."""
+    import pb_bss.distribution.gcacgmm as G
+    F, T, D, E, K = 20, 70, 4, 5, 3
+    y, labels = synth.structured_stft(F, T, D, K, seed=41)
+    rng = np.random.RandomState(5)
+    centers = rng.randn(K, E) * 2.0
+    emb = centers[labels] + 0.7 * rng.randn(F, T, E)           # (F, T, E): class-dependent embedding clouds
+    init = synth.init_affiliation(F, K, T, seed=3)
+    sal = rng.uniform(0.3, 1.0, size=(F, T))
+    cases = {
+        'spherical': dict(),
+        'diagonal_kt': dict(covariance_type='diagonal', weight_constant_axis=(-3,)),
+        'spherical_k_inline': dict(weight_constant_axis=(-3, -1), inline_permutation_alignment=True),
+        'spherical_sal_weights': dict(saliency=sal, spatial_weight=0.7, spectral_weight=1.3),
+    }
+    out = dict(y=y, embedding=emb, init=init, saliency=sal)
+    for name, kw in cases.items():
+        model = G.GCACGMMTrainer().fit(y, emb, initialization=init, iterations=4, **kw)
+        out[f'{name}_weight'] = np.asarray(model.weight)
+        out[f'{name}_mean'] = model.gaussian.mean
+        out[f'{name}_gcov'] = model.gaussian.covariance
+        out[f'{name}_eigenvalues'] = model.cacg.covariance_eigenvalues
+        out[f'{name}_covariance'] = model.cacg.covariance
+        out[f'{name}_affiliation'] = model.predict(y, emb)
+    np.savez_compressed(os.path.join(OUT, 'gcacgmm.npz'), **out)
+
+
 def make_initializer(ref):
     """pb_bss.initializer: iid draws after np.random.seed(0), flag, deflationSeed (deflation.py:6-89)."""
     import pb_bss.initializer as RI
@@ -366,6 +395,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'permutation':
         make_permutation(ref)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'gcacgmm':
+        make_gcacgmm(ref)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'coupled':
         make_cacgmm_coupled(ref)
         make_cwmm_coupled(ref)
@@ -380,6 +412,7 @@ def main():
     make_beamformer(ref)
     make_bf_wrapper(ref)
     make_initializer(ref)
+    make_gcacgmm(ref)
     make_full_size(ref)
     total = 0
     for n in sorted(os.listdir(OUT)):

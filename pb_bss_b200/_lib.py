@@ -65,6 +65,12 @@ SIGNATURES = {
     'pbb_souden': (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     'pbb_blind_analytic_normalization': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_dhtv_scratch_doubles': (_sz, [_i, _i, ctypes.POINTER(_i), _i]),
+    'pbb_cacg_log_pdf': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    'pbb_gaussian_log_pdf': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'pbb_gaussian_fit_scratch_doubles': (ctypes.c_size_t, [_i, _i, _i]),
+    'pbb_gaussian_fit': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'pbb_log_pdf_to_affiliation': (_i, [_vp, _vp, _d, _d, _vp, _i, _vp, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'pbb_class_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'pbb_dhtv_mapping': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _vp]),
     'pbb_dhtv_mapping_ex': (_i, [_vp, _i, _i, _i, ctypes.POINTER(_i), _i, _vp, _vp, _vp, _i, _i, _vp]),
     'pbb_apply_mapping': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -8,7 +8,7 @@ OUT=${PBB_OUT:-../libpbb.so}
 BUILD=${PBB_BUILD_DIR:-build}
 mkdir -p $BUILD
 pids=()
-for src in api_cacgmm api_linalg api_dhtv prof; do
+for src in api_cacgmm api_linalg api_dhtv api_integration prof; do
   if [ ! -f $BUILD/$src.o ] || [ $src.cu -nt $BUILD/$src.o ] || [ -n "$(find . -maxdepth 1 -name '*.cuh' -newer $BUILD/$src.o)" ] || [ ../../include/pbb.h -nt $BUILD/$src.o ]; then
     ( $NVCC $FLAGS -c $src.cu -o $BUILD/$src.o > $BUILD/$src.log 2>&1 || { cat $BUILD/$src.log; exit 1; } ) &
     pids+=($!)

@@ -6,3 +6,5 @@ from .complex_angular_central_gaussian import (  # noqa: F401
 from .cacgmm import CACGMM, CACGMMTrainer  # noqa: F401
 from .complex_watson import ComplexWatson, ComplexWatsonTrainer  # noqa: F401
 from .cwmm import CWMM, CWMMTrainer  # noqa: F401
+from .gaussian import DiagonalGaussian, SphericalGaussian  # noqa: F401
+from .gcacgmm import GCACGMM, GCACGMMTrainer  # noqa: F401
