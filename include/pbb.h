@@ -179,7 +179,9 @@ int pbb_cacg_log_pdf(const double* quadratic, const double* eigenvalues, int F, 
  * embedding (F, T, E), mean / precision_cholesky (K, E) (spherical: the scalar repeated E times), log_det (K)
  * -> log_pdf (F, K, T).  E <= 64.  diagonal != 0 evaluates the reference's DiagonalGaussian expression, whose einsum
  * '...dD,...nD->...nd' (gaussian.py:79-87) contracts precision_cholesky[d][:] of EVERY class d with the centred
- * observation and sums the squares over d -- reproduced as is, because the model is a drop-in. */
+ * observation and sums the squares over d -- reproduced as is, because the model is a drop-in.  diagonal == 2:
+ * VonMisesFisher.log_pdf (von_mises_fisher.py:66-81) for the vMF + cACG model: precision_cholesky[k][0] carries the
+ * concentration, log_det[k] the log normaliser; out = concentration <mean, x / max(||x||, tiny)> - log_norm. */
 int pbb_gaussian_log_pdf(const double* embedding, const double* mean,
                          const double* precision_cholesky, const double* log_det,
                          int F, int T, int E, int K, int diagonal, double* log_pdf,

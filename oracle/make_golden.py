@@ -357,6 +357,23 @@ def make_gcacgmm(ref):
         out[f'{name}_covariance'] = model.cacg.covariance
         out[f'{name}_affiliation'] = model.predict(y, emb)
     np.savez_compressed(os.path.join(OUT, 'gcacgmm.npz'), **out)
+    # the same problem with the von Mises-Fisher spectral model (vmfcacgmm.py:34-301)
+    import pb_bss.distribution.vmfcacgmm as V
+    vcases = {
+        'vmf': dict(),
+        'vmf_kt_inline': dict(weight_constant_axis=(-3,), inline_permutation_alignment=True, max_concentration=50),
+        'vmf_sal': dict(saliency=sal, spatial_weight=0.6, spectral_weight=1.2, weight_constant_axis=(-3, -1)),
+    }
+    vout = dict(y=y, embedding=emb, init=init, saliency=sal)
+    for name, kw in vcases.items():
+        model = V.VMFCACGMMTrainer().fit(y, emb, initialization=init, iterations=4, **kw)
+        vout[f'{name}_weight'] = np.asarray(model.weight)
+        vout[f'{name}_mean'] = model.vmf.mean
+        vout[f'{name}_concentration'] = model.vmf.concentration
+        vout[f'{name}_eigenvalues'] = model.cacg.covariance_eigenvalues
+        vout[f'{name}_covariance'] = model.cacg.covariance
+        vout[f'{name}_affiliation'] = model.predict(y, emb)
+    np.savez_compressed(os.path.join(OUT, 'vmfcacgmm.npz'), **vout)
 
 
 def make_initializer(ref):

@@ -62,6 +62,14 @@ __global__ void gaussian_log_pdf_kernel(const double* __restrict__ x, const doub
   const double c0 = -0.5 * (double)E * log(2.0 * 3.14159265358979323846);
   for (int k = 0; k < K; ++k) {
     double s = 0.0;
+    if (diagonal == 2) {
+      // von Mises-Fisher (von_mises_fisher.py:66-81): concentration * <mean, x / max(||x||, tiny)> - log_norm;
+      // pc[k][0] = concentration, log_det[k] = log_norm
+      double dot = 0.0, n2 = 0.0;
+      for (int e = 0; e < E; ++e) { dot += sm[k * E + e] * xe[e]; n2 += xe[e] * xe[e]; }
+      out[((size_t)f * K + k) * T + t] = sm[K * E + k * E] * (dot / fmax(sqrt(n2), kTiny)) - log_det[k];
+      continue;
+    }
     if (diagonal) {
       for (int d = 0; d < K; ++d) {
         double w = 0.0;

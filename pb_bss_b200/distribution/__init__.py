@@ -8,3 +8,5 @@ from .complex_watson import ComplexWatson, ComplexWatsonTrainer  # noqa: F401
 from .cwmm import CWMM, CWMMTrainer  # noqa: F401
 from .gaussian import DiagonalGaussian, SphericalGaussian  # noqa: F401
 from .gcacgmm import GCACGMM, GCACGMMTrainer  # noqa: F401
+from .von_mises_fisher import VonMisesFisher  # noqa: F401
+from .vmfcacgmm import VMFCACGMM, VMFCACGMMTrainer  # noqa: F401

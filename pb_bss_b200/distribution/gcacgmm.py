@@ -50,6 +50,90 @@ def _unit_norm_obs(observation):
     return od.contiguous()
 
 
+def spatial_log_pdf(cacg, od):
+    """Quadratic form and cACG log pdf (F, K, T) of the device observation (cacg.py:167-203)."""
+    F, T, D = od.shape
+    probe = CACGMM(weight=np.full([cacg.covariance_eigenvalues.shape[-2], 1], 1.0), cacg=cacg)
+    _, q, _, _ = probe._run_predict(od, None, 0., want_aff=False, want_q=True)
+    lam = _device.to_device(cacg.covariance_eigenvalues, torch.float64).contiguous()
+    K = lam.shape[-2]
+    lp = _device.empty((F, K, T), torch.float64)
+    lib = _lib.load()
+    _lib.check(lib.pbb_cacg_log_pdf(_device.ptr(q.contiguous()), _device.ptr(lam), F, K, T, D, _device.ptr(lp),
+                                    _device.stream_ptr()), 'pbb_cacg_log_pdf')
+    return q, lp
+
+
+def integrated_posterior(model, spectral, od, affiliation_eps, inline_permutation_alignment):
+    """Posterior of an integrated model (gcacgmm.py:86-128, vmfcacgmm.py:66-97): spatial_weight * cACG log pdf +
+    spectral_weight * spectral log pdf, mixture weights, optional per-bin pairing of the two models' classes."""
+    F, T, D = od.shape
+    quadratic_form, spatial = spatial_log_pdf(model.cacg, od)
+    K = spatial.shape[1]
+    assert spectral.shape == spatial.shape, (spectral.shape, spatial.shape)
+    mode = _weight_layout(model.weight_constant_axis)
+    w = None if mode == _lib.WEIGHT_CONST else _device.to_device(model.weight, torch.float64).contiguous()
+    aff = _device.empty((F, K, T), torch.float64)
+    lib = _lib.load()
+    _lib.check(lib.pbb_log_pdf_to_affiliation(
+        _device.ptr(spatial), _device.ptr(spectral), float(model.spatial_weight), float(model.spectral_weight),
+        _device.ptr(w), mode, None, float(affiliation_eps), int(bool(inline_permutation_alignment)), F, K, T,
+        _device.ptr(aff), None, _device.stream_ptr()), 'pbb_log_pdf_to_affiliation')
+    return aff, quadratic_form
+
+
+def class_weights(masked, weight_constant_axis):
+    """Mixture weights of an integrated model from the masked affiliations (F, K, T) (gcacgmm.py:283-291)."""
+    F, K, T = masked.shape
+    lib = _lib.load()
+    mode = _weight_layout(weight_constant_axis)
+    if mode == _lib.WEIGHT_CONST:
+        return 1 / K
+    if mode == _lib.WEIGHT_TIME:
+        weight = _device.empty((F, K), torch.float64)
+        _lib.check(lib.pbb_class_weight(_device.ptr(masked), F, K, T, _device.ptr(weight), _device.stream_ptr()),
+                   'pbb_class_weight')
+        return weight
+    w_kt = _device.empty((K, T), torch.float64)
+    w_k = _device.empty((K,), torch.float64)
+    _lib.check(lib.pbb_mixture_weight_over_bins(
+        _device.ptr(masked), F, K, T, int(mode == _lib.WEIGHT_TIED) | 2, _device.ptr(w_kt), _device.ptr(w_k),
+        _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
+    return w_kt if mode == _lib.WEIGHT_TIED_TIME else w_k
+
+
+def cacg_m_step(od, affiliation, quadratic_form, sal, hermitize, covariance_norm, eigenvalue_floor, what):
+    """cACG of every (bin, class) from the affiliations: the cACGMM M-step kernel (cacg.py:253-342)."""
+    F, T, D = od.shape
+    K = affiliation.shape[1]
+    lib = _lib.load()
+    V = _device.empty((F, K, D, D), torch.complex128)
+    lam = _device.empty((F, K, D), torch.float64)
+    w_unused = _device.empty((F, K), torch.float64)
+    status = _device.empty((1,), torch.int32)
+    opts = _lib.CacgmmOptions(
+        iterations=1, covariance_norm=_NORMS[covariance_norm], weight_mode=_lib.WEIGHT_TIME,
+        hermitize=int(bool(hermitize)), affiliation_eps=0., eigenvalue_floor=float(eigenvalue_floor),
+        frames_per_block=0, reserved=0)
+    nbytes = lib.pbb_cacgmm_workspace_bytes(F, T, D, K)
+    ws = _device.workspace(nbytes)
+    _lib.check(lib.pbb_cacgmm_mstep(
+        _device.ptr(od), _device.complex_dtype_code(od), F, T, D, K, _device.ptr(affiliation.contiguous()),
+        _device.ptr(quadratic_form), _device.ptr(sal), ctypes.byref(opts), _device.ptr(V), _device.ptr(lam),
+        _device.ptr(w_unused), _device.ptr(ws), nbytes, _device.ptr(status), _device.stream_ptr()),
+        'pbb_cacgmm_mstep')
+    _status_check(status, what)
+    return ComplexAngularCentralGaussian(covariance_eigenvectors=V, covariance_eigenvalues=lam)
+
+
+def model_to_host(model):
+    model.weight = _device.to_host(model.weight, True) if _device.is_tensor(model.weight) else model.weight
+    model.cacg = ComplexAngularCentralGaussian(
+        covariance_eigenvectors=_device.to_host(model.cacg.covariance_eigenvectors, True),
+        covariance_eigenvalues=_device.to_host(model.cacg.covariance_eigenvalues, True))
+    return model
+
+
 @dataclass
 class GCACGMM(_ProbabilisticModel):
     weight: np.array = None  # Shape (), (K,), (F, K), (K, T)
@@ -68,35 +152,10 @@ class GCACGMM(_ProbabilisticModel):
         affiliation, _ = self._predict(od, ed)
         return _device.to_host(affiliation, like_numpy)
 
-    def _spatial(self, od):
-        """Quadratic form and cACG log pdf (F, K, T) of the device observation."""
-        F, T, D = od.shape
-        probe = CACGMM(weight=np.full([self.cacg.covariance_eigenvalues.shape[-2], 1], 1.0), cacg=self.cacg)
-        _, q, _, _ = probe._run_predict(od, None, 0., want_aff=False, want_q=True)
-        lam = _device.to_device(self.cacg.covariance_eigenvalues, torch.float64).contiguous()
-        K = lam.shape[-2]
-        lp = _device.empty((F, K, T), torch.float64)
-        lib = _lib.load()
-        _lib.check(lib.pbb_cacg_log_pdf(_device.ptr(q.contiguous()), _device.ptr(lam), F, K, T, D, _device.ptr(lp),
-                                        _device.stream_ptr()), 'pbb_cacg_log_pdf')
-        return q, lp
-
     def _predict(self, od, ed, affiliation_eps=0., inline_permutation_alignment=False):
         """gcacgmm.py:70-128 on device tensors -> (affiliation, quadratic_form), both (F, K, T)."""
-        F, T, D = od.shape
-        quadratic_form, spatial = self._spatial(od)
-        spectral = self.gaussian.log_pdf_fkt(ed)
-        K = spatial.shape[1]
-        assert spectral.shape == spatial.shape, (spectral.shape, spatial.shape)
-        mode = _weight_layout(self.weight_constant_axis)
-        w = None if mode == _lib.WEIGHT_CONST else _device.to_device(self.weight, torch.float64).contiguous()
-        aff = _device.empty((F, K, T), torch.float64)
-        lib = _lib.load()
-        _lib.check(lib.pbb_log_pdf_to_affiliation(
-            _device.ptr(spatial), _device.ptr(spectral), float(self.spatial_weight), float(self.spectral_weight),
-            _device.ptr(w), mode, None, float(affiliation_eps), int(bool(inline_permutation_alignment)), F, K, T,
-            _device.ptr(aff), None, _device.stream_ptr()), 'pbb_log_pdf_to_affiliation')
-        return aff, quadratic_form
+        return integrated_posterior(self, self.gaussian.log_pdf_fkt(ed), od, affiliation_eps,
+                                    inline_permutation_alignment)
 
 
 class GCACGMMTrainer:
@@ -133,12 +192,7 @@ class GCACGMMTrainer:
             model = self._m_step(od, ed, quadratic_form, affiliation, sal, hermitize, covariance_norm,
                                  eigenvalue_floor, covariance_type, fixed_covariance, weight_constant_axis,
                                  spatial_weight, spectral_weight)
-        if like_numpy:
-            model.weight = _device.to_host(model.weight, True) if _device.is_tensor(model.weight) else model.weight
-            model.cacg = ComplexAngularCentralGaussian(
-                covariance_eigenvectors=_device.to_host(model.cacg.covariance_eigenvectors, True),
-                covariance_eigenvalues=_device.to_host(model.cacg.covariance_eigenvalues, True))
-        return model
+        return model_to_host(model) if like_numpy else model
 
     def fit_predict(self, observation, embedding, **kwargs):
         """Fit a model, then return the posterior affiliations (gcacgmm.py:229-267)."""
@@ -148,47 +202,14 @@ class GCACGMMTrainer:
     def _m_step(self, od, ed, quadratic_form, affiliation, sal, hermitize, covariance_norm, eigenvalue_floor,
                 covariance_type, fixed_covariance, weight_constant_axis, spatial_weight, spectral_weight):
         """gcacgmm.py:269-333 on device tensors."""
-        F, T, D = od.shape
-        K = affiliation.shape[1]
-        lib = _lib.load()
         masked = affiliation if sal is None else (affiliation * sal[:, None, :]).contiguous()
-        mode = _weight_layout(weight_constant_axis)
-        if mode == _lib.WEIGHT_CONST:
-            weight = 1 / K
-        elif mode == _lib.WEIGHT_TIME:
-            weight = _device.empty((F, K), torch.float64)
-            _lib.check(lib.pbb_class_weight(_device.ptr(masked), F, K, T, _device.ptr(weight), _device.stream_ptr()),
-                       'pbb_class_weight')
-        else:
-            w_kt = _device.empty((K, T), torch.float64)
-            w_k = _device.empty((K,), torch.float64)
-            _lib.check(lib.pbb_mixture_weight_over_bins(
-                _device.ptr(masked), F, K, T, int(mode == _lib.WEIGHT_TIED) | 2, _device.ptr(w_kt), _device.ptr(w_k),
-                _device.stream_ptr()), 'pbb_mixture_weight_over_bins')
-            weight = w_kt if mode == _lib.WEIGHT_TIED_TIME else w_k
+        weight = class_weights(masked, weight_constant_axis)
         gaussian = gaussian_fit_fkt(ed, masked, covariance_type)
         if fixed_covariance is not None:
             assert np.shape(fixed_covariance) == np.shape(gaussian.covariance), (
                 f'{np.shape(fixed_covariance)} != {np.shape(gaussian.covariance)}')
             gaussian = gaussian.__class__(mean=gaussian.mean, covariance=np.asarray(fixed_covariance))
-        # cACG of every (bin, class): the cACGMM M-step kernel with the masked affiliations as its weights
-        V = _device.empty((F, K, D, D), torch.complex128)
-        lam = _device.empty((F, K, D), torch.float64)
-        w_unused = _device.empty((F, K), torch.float64)
-        status = _device.empty((1,), torch.int32)
-        opts = _lib.CacgmmOptions(
-            iterations=1, covariance_norm=_NORMS[covariance_norm], weight_mode=_lib.WEIGHT_TIME,
-            hermitize=int(bool(hermitize)), affiliation_eps=0., eigenvalue_floor=float(eigenvalue_floor),
-            frames_per_block=0, reserved=0)
-        nbytes = lib.pbb_cacgmm_workspace_bytes(F, T, D, K)
-        ws = _device.workspace(nbytes)
-        _lib.check(lib.pbb_cacgmm_mstep(
-            _device.ptr(od), _device.complex_dtype_code(od), F, T, D, K, _device.ptr(affiliation.contiguous()),
-            _device.ptr(quadratic_form), _device.ptr(sal), ctypes.byref(opts), _device.ptr(V), _device.ptr(lam),
-            _device.ptr(w_unused), _device.ptr(ws), nbytes, _device.ptr(status), _device.stream_ptr()),
-            'pbb_cacgmm_mstep')
-        _status_check(status, 'GCACGMMTrainer._m_step')
-        return GCACGMM(
-            weight=weight, weight_constant_axis=weight_constant_axis, gaussian=gaussian,
-            cacg=ComplexAngularCentralGaussian(covariance_eigenvectors=V, covariance_eigenvalues=lam),
-            spatial_weight=spatial_weight, spectral_weight=spectral_weight)
+        cacg = cacg_m_step(od, affiliation, quadratic_form, sal, hermitize, covariance_norm, eigenvalue_floor,
+                           'GCACGMMTrainer._m_step')
+        return GCACGMM(weight=weight, weight_constant_axis=weight_constant_axis, gaussian=gaussian, cacg=cacg,
+                       spatial_weight=spatial_weight, spectral_weight=spectral_weight)
