@@ -10,10 +10,21 @@
  * pb_bss_b200/_lib.py does.
  *
  * Conventions
- *  - every pointer is a DEVICE pointer owned by the caller (the library never
- *    allocates persistent memory and never frees caller memory);
+ *  - every pointer is a DEVICE pointer owned by the caller and the library never frees
+ *    caller memory (pbb_cacgmm_fit additionally accepts PINNED host pointers, see there).
+ *    The library itself owns three small things per device, created on first use and kept
+ *    for the life of the process: a non-blocking side stream with two events (streamed
+ *    upload of pbb_cacgmm_fit), a cache of at most 16 task-order tables (4 bytes per task,
+ *    streamed upload only) and the occupancy numbers of its persistent kernels;
  *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered
- *    and asynchronous, nothing here synchronises the device;
+ *    and asynchronous, no entry synchronises the device or the stream;
+ *  - limits: D < 35, K < 20 (the reference asserts the same, cacgmm.py:197,249-250);
+ *    pbb_streamed_task_order packs the bin into 16 bits (F <= 65535; pbb_cacgmm_fit only uses
+ *    such a table for F <= 4096 and schedules larger problems without it);
+ *  - thread safety: entries may be called concurrently from several host threads on
+ *    different streams.  pbb_last_error() is thread-local.  Two streamed fits (pinned-host
+ *    input) on the SAME device are serialised while they enqueue, because they share the
+ *    side stream; everything else only reads library state;
  *  - return value: 0 = ok, -i = argument i (1-based) invalid (LAPACK INFO<0
  *    convention, cf. get_gev_vector.pyx:130-147), > 0 = CUDA runtime error
  *    code; pbb_last_error() gives the message (thread-local);

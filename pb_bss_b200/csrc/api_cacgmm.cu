@@ -355,6 +355,7 @@ static int classify_pointer(const void* p, const void** dev_alias, bool* is_host
 // side stream + events for the upload that overlaps the EM kernel (one set per process)
 typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct LoadStream {
+  std::mutex mu;  // one streamed fit per device enqueues at a time (the side stream and its events are shared)
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   StreamWaitValue32Fn wait_value = nullptr;  // cuStreamWaitValue32, resolved through the runtime
@@ -362,6 +363,8 @@ struct LoadStream {
 };
 static int get_load_stream(LoadStream** out) {
   static LoadStream ls[16];
+  static std::mutex init_mu;
+  std::lock_guard<std::mutex> init_lk(init_mu);
   int dev = 0;
   PBB_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16) { set_error("device index %d out of range", dev); return 1; }
@@ -606,6 +609,15 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
   const bool lean_ok = fast_sm && (K - 1) * D * (log10(1.0 / opt->eigenvalue_floor) + 1.0) < 290.0;
   const bool full = saliency != nullptr || activity != nullptr || !lean_ok || init_aff == nullptr;
   const int layout = persistent && use_ls_kernel(D, full) ? 1 : 0;
+  // Thread safety: the side stream and the fork / join events of the streamed upload exist once per device, so two
+  // host threads enqueueing streamed fits on the same device are serialised from here to the end of the call
+  // (the enqueue only; the GPU work of the two fits still overlaps as far as their streams allow).
+  std::unique_lock<std::mutex> stream_lock;
+  if (streamed) {
+    LoadStream* lsm = nullptr;
+    if ((r = get_load_stream(&lsm))) return r;
+    stream_lock = std::unique_lock<std::mutex>(lsm->mu);
+  }
   if (streamed) {
     // flags[bin] = -1 until the bin has arrived
     PBB_CUDA(cudaMemsetAsync(ws.flags, 0, (size_t)(F + 1) * sizeof(int) + 16 * sizeof(unsigned long long) + 8, st));
