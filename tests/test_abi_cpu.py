@@ -78,8 +78,9 @@ def test_weight_axis_mapping():
     assert _weight_mode((-3,), 3) == _lib.WEIGHT_TIED_TIME
     assert _weight_mode((-3, -1), 3) == _lib.WEIGHT_TIED
     assert _weight_mode((-1, -3), 3) == _lib.WEIGHT_TIED
-    with pytest.raises(NotImplementedError):
-        _weight_mode((-3,), 4)  # more than one independent dim
+    # more than one independent dim: the bins (axis -3) are tied, the dims in front stay independent fits
+    assert _weight_mode((-3,), 4) == _lib.WEIGHT_TIED_TIME
+    assert _weight_mode((-3, -1), 5) == _lib.WEIGHT_TIED
     with pytest.raises(NotImplementedError):
         _weight_mode((-4, -1), 4)
 
