@@ -181,6 +181,13 @@ __device__ __forceinline__ void dhtv_assign(double* __restrict__ score, int K, i
   }
 }
 
+#ifdef PBB_PHASE_TIMING
+__device__ unsigned long long g_dhtv_phase[8];
+#define DH_PH(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long _t = clock64(); g_dhtv_phase[i] += (unsigned long long)(_t - _tp); _tp = _t; } } while (0)
+#else
+#define DH_PH(i) do { } while (0)
+#endif
+
 // Grid-wide barrier of a cooperative launch (all CTAs are resident): a monotonic arrival counter, one atomic and a
 // short acquire spin per CTA -- about a third of the latency of cooperative_groups' grid.sync() here.
 __device__ __forceinline__ void dhtv_grid_barrier(unsigned* counter, unsigned& generation) {
@@ -198,21 +205,41 @@ __device__ __forceinline__ void dhtv_grid_barrier(unsigned* counter, unsigned& g
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ feat, double* __restrict__ partial,
-                                                        int* __restrict__ changed, const int* __restrict__ plan,
-                                                        int nplan, int K, int F, int T,
-                                                        long long* __restrict__ mapping, unsigned* __restrict__ bar,
-                                                        int metric, int optimal) {
+// block_sum over the FIRST 128 threads only, in the order of the 128-thread launch pair (dhtv_assign_kernel): the
+// centroid norms -- and with them every score and the integer mapping -- stay bit-identical whatever the block size
+__device__ inline double block_sum_first128(double v, double* red) {
+  v = warp_sum(threadIdx.x < 128 ? v : 0.0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0 && warp < 4) red[warp] = v;
+  __syncthreads();
+  return ((red[0] + red[1]) + red[2]) + red[3];
+}
+
+constexpr int kDhtvCoopMaxWarps = 16;
+
+// One CTA per bin of the segment, one WARP per (reference class, mask class) score: a single warp per bin spends
+// ~25k cycles per iteration on its K^2 dot products and the assignment (latency of one dependent instruction stream);
+// spread over K^2 warps the bin takes ~2k.
+__global__ void __launch_bounds__(32 * kDhtvCoopMaxWarps) dhtv_coop_kernel(
+    double* __restrict__ feat, double* __restrict__ partial, int* __restrict__ changed, const int* __restrict__ plan,
+    int nplan, int K, int F, int T, long long* __restrict__ mapping, unsigned* __restrict__ bar, int metric,
+    int optimal) {
   // metric: 1 = cos (features and centroid L2-normalised over time, score = inner product), 0 = multiply (inner
   // product of the raw masks), 2 = euclidean (score = -distance), permutation_alignment.py:309-340,380-420
   unsigned generation = 0;
+#ifdef PBB_PHASE_TIMING
+  long long _tp = clock64();
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* cent = reinterpret_cast<double*>(smem_raw);  // [K][T]
   __shared__ double red[4];
   __shared__ double cnorm[kDhtvMaxK];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double score_s[kDhtvMaxK * kDhtvMaxK];
+  __shared__ int perm_s[kDhtvMaxK];
+  __shared__ int ident_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
-  const int gwarps = gridDim.x * 4, gwarp = blockIdx.x * 4 + warp;
   int idx = 0;
   for (int p = 0; p < nplan; ++p) {
     const int iters = plan[3 * p], start = plan[3 * p + 1], end = plan[3 * p + 2];
@@ -234,11 +261,13 @@ __global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ fea
         for (; f < f1; ++f) s0 += feat[((size_t)k * F + f) * T + t];
         partial[(size_t)sl * K * T + i] = (s0 + s1) + (s2 + s3);
       }
+      DH_PH(0);  // phase A
       dhtv_grid_barrier(bar, generation);
-      // ---- phase B: one warp per bin (dhtv_assign_kernel); CTAs without a bin skip the centroid ----
-      if (blockIdx.x * 4 < n) {
+      DH_PH(1);  // barrier 1
+      // ---- phase B: one CTA per bin (dhtv_assign_kernel); CTAs without a bin skip the centroid ----
+      if ((int)blockIdx.x < n) {
         const double inv_n = 1.0 / (double)n;
-#pragma unroll 4
+#pragma unroll 2
         for (int i = tid; i < K * T; i += blockDim.x) {
           double v[kDhtvSlices];
 #pragma unroll
@@ -249,69 +278,80 @@ __global__ void __launch_bounds__(128) dhtv_coop_kernel(double* __restrict__ fea
           cent[i] = s * inv_n;
         }
         __syncthreads();
+        DH_PH(2);  // centroid combine
         if (metric == 1) {
           for (int k = 0; k < K; ++k) {
             double s = 0.0;
-            for (int t = tid; t < T; t += blockDim.x) { const double c = cent[k * T + t]; s += c * c; }
-            const double nn = sqrt(block_sum(s, red));
+            if (tid < 128)
+              for (int t = tid; t < T; t += 128) { const double c = cent[k * T + t]; s += c * c; }
+            const double nn = sqrt(block_sum_first128(s, red));
             if (tid == 0) cnorm[k] = fmax(nn, kTiny);
           }
           __syncthreads();
           for (int i = tid; i < K * T; i += blockDim.x) cent[i] = cent[i] / cnorm[i / T];
           __syncthreads();
         }
-        for (int f = start + gwarp; f < end; f += gwarps) {
-          // scores[kr][km] = <centroid kr, feature km of this bin>: the feature row is fetched 16 values per lane
-          // at a time with every load in flight (the plain loop is a chain of dependent L2 round trips); each
-          // (kr, km) sum still runs over t in ascending order, so the result is bit-identical to dhtv_assign_kernel
-          double score[kDhtvMaxK * kDhtvMaxK];
-          for (int i = 0; i < K * K; ++i) score[i] = 0.0;
-          for (int c0 = 0; c0 < T; c0 += 512) {
-            for (int km = 0; km < K; ++km) {
+        DH_PH(3);  // centroid norms
+        for (int f = start + blockIdx.x; f < end; f += gridDim.x) {
+          // score[kr][km] = <centroid kr, feature km of this bin> by warp (kr, km): 16 values per lane at a time with
+          // every load in flight; the sum runs over t in ascending order per lane, then the usual warp reduction --
+          // bit-identical to dhtv_assign_kernel
+          for (int pair = warp; pair < K * K; pair += nwarps) {
+            const int kr = pair / K, km = pair - kr * K;
+            const double* __restrict__ row = feat + ((size_t)km * F + f) * T;
+            double sacc = 0.0;
+            for (int c0 = 0; c0 < T; c0 += 512) {
               double v[16];
-              const double* __restrict__ row = feat + ((size_t)km * F + f) * T;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int t = c0 + lane + 32 * j;
                 v[j] = t < T ? __ldcg(row + t) : 0.0;
               }
-              for (int kr = 0; kr < K; ++kr) {
-                double sacc = score[kr * K + km];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int t = c0 + lane + 32 * j;
-                  if (t < T) {
-                    if (metric == 2) { const double dlt = v[j] - cent[kr * T + t]; sacc += dlt * dlt; }
-                    else sacc += v[j] * cent[kr * T + t];
-                  }
+              for (int j = 0; j < 16; ++j) {
+                const int t = c0 + lane + 32 * j;
+                if (t < T) {
+                  if (metric == 2) { const double dlt = v[j] - cent[kr * T + t]; sacc += dlt * dlt; }
+                  else sacc += v[j] * cent[kr * T + t];
                 }
-                score[kr * K + km] = sacc;
               }
             }
+            sacc = warp_sum(sacc);
+            if (metric == 2) sacc = -sqrt(sacc);  // the minus turns the distance into a similarity (:412-418)
+            if (lane == 0) score_s[pair] = sacc;
           }
-          for (int i = 0; i < K * K; ++i) {
-            score[i] = warp_sum(score[i]);
-            if (metric == 2) score[i] = -sqrt(score[i]);  // the minus turns the distance into a similarity (:412-418)
+          __syncthreads();
+          DH_PH(4);  // scores
+          if (tid == 0) {
+            double sc[kDhtvMaxK * kDhtvMaxK];
+            int perm[kDhtvMaxK];
+            for (int i = 0; i < K * K; ++i) sc[i] = score_s[i];
+            dhtv_assign(sc, K, optimal, perm);
+            bool ident = true;
+            for (int k = 0; k < K; ++k) { perm_s[k] = perm[k]; ident = ident && perm[k] == k; }
+            ident_s = ident ? 1 : 0;
+            if (!ident) {
+              long long mv[kDhtvMaxK];
+              for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
+              for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
+              changed[idx] = 1;
+            }
           }
-          int perm[kDhtvMaxK];
-          dhtv_assign(score, K, optimal, perm);
-          bool ident = true;
-          for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
-          if (ident) continue;
-          for (int t = lane; t < T; t += 32) {
-            double v[kDhtvMaxK];
-            for (int k = 0; k < K; ++k) v[k] = feat[((size_t)k * F + f) * T + t];
-            for (int k = 0; k < K; ++k) feat[((size_t)k * F + f) * T + t] = v[perm[k]];
+          __syncthreads();
+          DH_PH(5);  // assignment
+          if (!ident_s) {
+            for (int t = tid; t < T; t += blockDim.x) {
+              double v[kDhtvMaxK];
+              for (int k = 0; k < K; ++k) v[k] = feat[((size_t)k * F + f) * T + t];
+              for (int k = 0; k < K; ++k) feat[((size_t)k * F + f) * T + t] = v[perm_s[k]];
+            }
           }
-          if (lane == 0) {
-            long long mv[kDhtvMaxK];
-            for (int k = 0; k < K; ++k) mv[k] = mapping[(size_t)k * F + f];
-            for (int k = 0; k < K; ++k) mapping[(size_t)k * F + f] = mv[perm[k]];
-            changed[idx] = 1;
-          }
+          __syncthreads();
         }
       }
+      DH_PH(6);  // permutation / rest of phase B
       dhtv_grid_barrier(bar, generation);
+      DH_PH(7);  // barrier 2
       if (__ldcg(changed + idx) == 0) {  // nothing moved: the segment has converged (:352-353)
         idx += iters - it;
         break;
@@ -499,15 +539,30 @@ int pbb_dhtv_mapping_ex(const double* mask, int K, int F, int T, const int* plan
     const size_t smem = (size_t)K * T * sizeof(double);
     PBB_CUDA(cudaFuncSetAttribute(dhtv_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0, sms = 0;
-    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dhtv_coop_kernel, 128, smem));
+    int warps = K * K < kDhtvCoopMaxWarps ? K * K : kDhtvCoopMaxWarps;
+    if (warps < 4) warps = 4;  // the centroid norms are summed by the first 128 threads
+    const int threads = 32 * warps;
+    PBB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dhtv_coop_kernel, threads, smem));
     PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int grid = (kDhtvSlices * K * T + 127) / 128;  // one phase-A element per thread
+    int widest = 1;  // one CTA per bin of the widest segment
+    for (int p = 0; p < nplan; ++p) widest = plan[3 * p + 2] - plan[3 * p + 1] > widest ? plan[3 * p + 2] - plan[3 * p + 1] : widest;
+    int grid = widest;
     if (grid > per_sm * sms) grid = per_sm * sms;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&features, (void*)&partial, (void*)&changed, (void*)&plan_dev, (void*)&nplan,
                     (void*)&K, (void*)&F, (void*)&T, (void*)&mapping, (void*)&bar, (void*)&metric, (void*)&algorithm};
     LaunchScope ls("dhtv_coop_kernel", st);
-    PBB_CUDA(cudaLaunchCooperativeKernel((const void*)dhtv_coop_kernel, dim3(grid), dim3(128), args, smem, st));
+    PBB_CUDA(cudaLaunchCooperativeKernel((const void*)dhtv_coop_kernel, dim3(grid), dim3(threads), args, smem, st));
+#ifdef PBB_PHASE_TIMING
+    {
+      unsigned long long ph[8], zero[8] = {0};
+      cudaStreamSynchronize(st);
+      cudaMemcpyFromSymbol(ph, g_dhtv_phase, sizeof(ph));
+      cudaMemcpyToSymbol(g_dhtv_phase, zero, sizeof(zero));
+      static const char* nm[8] = {"phase A", "barrier 1", "centroid combine", "centroid norms", "scores", "assignment", "permute/rest", "barrier 2"};
+      for (int i = 0; i < 8; ++i) fprintf(stderr, "[dhtv] %-18s %10llu cycles\n", nm[i], ph[i]);
+    }
+#endif
     return 0;
   }
   PBB_CHECK_ARG(metric == 1 && algorithm == 0, 10,

@@ -174,6 +174,7 @@ struct PersistSmem {
   CT zbuf[kStages][ROWS][kStageFrames];
   double2 A[K][NS];     // scatter matrix / its inverse
   double2 V[K][NS];     // eigenvectors (Jacobi fallback only)
+  double2 W[K][NS];     // complex Watson: second scratch of the top-eigenpair iteration
   double coef[2][K][NS];  // E-step form of the bin's model (double buffered: next task's model is prefetched)
   double xq[2][M][2 * K][32];  // partial quadratic forms, up to 2 frames per lane
   double S[K][NS + 1];  // scatter sums + sum of gamma
@@ -1097,17 +1098,22 @@ em_persistent_kernel(const PersistArgs a) {
           }
           __syncwarp();
           if (__any_sync(0xffffffffu, wbad) && lane == 0) atomicMax(a.status, bin + 1);
-          warp_jacobi_small<D>(A, sm.V[k], lane);
-          int best = 0;
-          double lmax = A[0].x;
-#pragma unroll
-          for (int d = 1; d < D; ++d) {
-            const double l = A[d * D + d].x;
-            if (l >= lmax) { lmax = l; best = d; }
-          }
           double2* mloc = reinterpret_cast<double2*>(sm.rot[k]);  // ((D+1)/2)*6 doubles >= 2*D, 16-byte aligned
-          __syncwarp();
-          for (int d = lane; d < D; d += 32) mloc[d] = sm.V[k][d * D + best];
+          double lmax;
+          // only the largest eigenpair is needed: repeated squaring, exact Jacobi when the spectrum is too close
+          if (!warp_top_eigenpair<D>(A, sm.V[k], sm.W[k], lane, &lmax, mloc)) {
+            __syncwarp();
+            warp_jacobi_small<D>(A, sm.V[k], lane);
+            int best = 0;
+            lmax = A[0].x;
+#pragma unroll
+            for (int d = 1; d < D; ++d) {
+              const double l = A[d * D + d].x;
+              if (l >= lmax) { lmax = l; best = d; }
+            }
+            __syncwarp();
+            for (int d = lane; d < D; d += 32) mloc[d] = sm.V[k][d * D + best];
+          }
           __syncwarp();
           cw_coef_from_mode(mloc, sm.tab, D, lane, a.coef + ((size_t)bin * K + k) * NS);
           if (lane == 0) {

@@ -218,6 +218,100 @@ __device__ inline int warp_jacobi_any(double2* __restrict__ A, double2* __restri
   }
 }
 
+// Largest eigenpair of a Hermitian positive semi-definite D x D matrix (D <= 8) WITHOUT a full eigendecomposition:
+// B <- A / tr A, then kTopSquarings times B <- B B / tr(B B), which is A^(2^n) up to scale and converges to the
+// projector v v^H at the rate (lambda_2 / lambda_1)^(2^n); v is the column of the largest diagonal entry, the
+// eigenvalue its Rayleigh quotient with the ORIGINAL A.  Accepted only if the residual |A v - lambda v|_inf is
+// below 1e-13 lambda (spectra with lambda_2 / lambda_1 > ~0.9995 fail that test): the caller then runs the
+// Jacobi solver, so the result is always as exact as np.linalg.eigh's.  A is left untouched; B, C: D x D scratch.
+// One lane per matrix entry (two for D = 8).  x_out: D entries in shared memory.
+constexpr int kTopSquarings = 16;
+template <int D>
+__device__ __forceinline__ bool warp_top_eigenpair(const double2* __restrict__ A, double2* __restrict__ B,
+                                                   double2* __restrict__ C, int lane, double* __restrict__ lambda,
+                                                   double2* __restrict__ x_out) {
+  constexpr int NS = D * D, PER = (NS + 31) / 32;
+  double tr = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) tr += A[d * D + d].x;
+  if (!(tr > 0.0) || !(tr < 1e300)) return false;
+  const double itr = 1.0 / tr;
+  for (int i = lane; i < NS; i += 32) B[i] = make_double2(A[i].x * itr, A[i].y * itr);
+  __syncwarp();
+#pragma unroll 1
+  for (int n = 0; n < kTopSquarings; ++n) {
+    double2 c[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const int i = lane + 32 * r;
+      c[r] = make_double2(0.0, 0.0);
+      if (i < NS) {
+        const int row = i / D, col = i - row * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double2 a = B[row * D + k], b = B[k * D + col];
+          c[r].x = fma(a.x, b.x, fma(-a.y, b.y, c[r].x));
+          c[r].y = fma(a.x, b.y, fma(a.y, b.x, c[r].y));
+        }
+        C[i] = c[r];
+      }
+    }
+    __syncwarp();
+    double t2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) t2 += C[d * D + d].x;
+    const double s = 1.0 / t2;
+    double change = 0.0;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const int i = lane + 32 * r;
+      if (i < NS) {
+        const double2 nb = make_double2(c[r].x * s, c[r].y * s);
+        change = fmax(change, fabs(nb.x - B[i].x) + fabs(nb.y - B[i].y));
+        B[i] = nb;
+      }
+    }
+    __syncwarp();
+    // B is a fixed point of the squaring (a projector) once nothing moves any more: stop early
+    if (n >= 4 && !__any_sync(0xffffffffu, change > 1e-16)) break;
+  }
+  // dominant column
+  int best = 0;
+  double bmax = B[0].x;
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const double v = B[d * D + d].x;
+    if (v > bmax) { bmax = v; best = d; }
+  }
+  double n2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) { const double2 v = B[d * D + best]; n2 += v.x * v.x + v.y * v.y; }
+  if (!(n2 > 0.0)) return false;
+  const double inv = rsqrt(n2);
+  if (lane < D) x_out[lane] = make_double2(B[lane * D + best].x * inv, B[lane * D + best].y * inv);
+  __syncwarp();
+  // y = A x (every lane computes all of it: D is tiny), lambda = Re(x^H y), residual
+  double2 y[D];
+  double lam = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    y[r] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double2 a = A[r * D + k], v = x_out[k];
+      y[r].x = fma(a.x, v.x, fma(-a.y, v.y, y[r].x));
+      y[r].y = fma(a.x, v.y, fma(a.y, v.x, y[r].y));
+    }
+    lam += x_out[r].x * y[r].x + x_out[r].y * y[r].y;
+  }
+  double res = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+    res = fmax(res, fabs(y[r].x - lam * x_out[r].x) + fabs(y[r].y - lam * x_out[r].y));
+  *lambda = lam;
+  return res <= 1e-13 * lam;
+}
+
 // rank of eigenvalue i in ascending order (stable), for i < D; lanes >= D get -1.
 // For D > 32 callers loop (i = lane, lane + 32, ...).
 __device__ inline int eig_rank(const double2* A, int D, int i) {

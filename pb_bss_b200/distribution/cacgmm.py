@@ -56,7 +56,11 @@ def _flatten_obs(y):
     return tuple(independent), F, N, D
 
 
-def _status_check(status, what):
+def _status_check(status, what, defer=None):
+    if defer is not None:
+        # coupled EM loop: keep the stream full, look at every status word once after the last iteration
+        defer.append((status, what))
+        return
     s = int(status.item())  # synchronises the stream
     if s != 0:
         # the reference asserts finiteness at cacg.py:127,326,333
@@ -86,7 +90,7 @@ class CACGMM(_ProbabilisticModel):
         return V, lam, w, K, _lib.WEIGHT_TIME
 
     def _run_predict(self, y, source_activity_mask, affiliation_eps,
-                     want_aff=True, want_q=False, want_ll=False):
+                     want_aff=True, want_q=False, want_ll=False, defer=None):
         like_numpy = not _device.is_tensor(y)
         yd = _device.to_device(y)
         code = _device.complex_dtype_code(yd)
@@ -111,7 +115,7 @@ class CACGMM(_ProbabilisticModel):
             float(affiliation_eps), _device.ptr(aff), _device.ptr(q),
             _device.ptr(ll), _device.ptr(ws), nbytes, _device.ptr(status),
             _device.stream_ptr()), 'pbb_cacgmm_predict')
-        _status_check(status, 'CACGMM.predict')
+        _status_check(status, 'CACGMM.predict', defer)
         shape = (*independent, K, N)
         if aff is not None:
             aff = _device.to_host(aff.reshape(shape), like_numpy)
@@ -360,10 +364,14 @@ class CACGMMTrainer:
         affiliation = init_dev.reshape(*independent, K, N) if init_dev is not None else None
         quadratic_form = None
         m_axis = (-1,) if tied else weight_constant_axis
+        # no host synchronisation inside the loop: the per-call status words are collected and read once at the end
+        pending = []
+        if source_activity_mask is not None and not _device.is_tensor(source_activity_mask):
+            source_activity_mask = _device.to_device(source_activity_mask)   # uploaded once, not per iteration
         for _ in range(iterations):
             if model is not None:
                 affiliation, quadratic_form, _, _ = model._run_predict(
-                    yd, source_activity_mask, affiliation_eps, want_q=True)
+                    yd, source_activity_mask, affiliation_eps, want_q=True, defer=pending)
                 if aligner is not None:
                     mask_kft = affiliation.permute(1, 0, 2).contiguous()
                     if F_all != F:  # the alignment needs every bin: gather, align replicated, keep the slice
@@ -377,7 +385,7 @@ class CACGMMTrainer:
             model = cacgmm_m_step(
                 yd, quadratic_form, affiliation, saliency=saliency, hermitize=hermitize,
                 covariance_norm=covariance_norm, eigenvalue_floor=eigenvalue_floor,
-                weight_constant_axis=m_axis)
+                weight_constant_axis=m_axis, defer=pending)
             if tied:
                 aff = affiliation.reshape(F, K, N)
                 if sal_w is not None:
@@ -393,6 +401,11 @@ class CACGMMTrainer:
                     w_kt = parallel.mean_over_all_bins(w_kt, F, F_all, bin_group)
                     w_k = parallel.mean_over_all_bins(w_k, F, F_all, bin_group)
                 model.weight = w_kt[None] if weight_mode == _lib.WEIGHT_TIED_TIME else w_k[None, :, None]
+        if pending:
+            words = torch.stack([st.reshape(()) for st, _ in pending]).cpu().tolist()   # the one synchronisation
+            for s_, (_, what) in zip(words, pending):
+                if s_ != 0:
+                    raise AssertionError(f'{what}: non-finite covariance / eigenvalues in bin {s_ - 1}')
         if like_numpy:
             model = CACGMM(
                 weight=_device.to_host(model.weight, True) if _device.is_tensor(model.weight) else model.weight,
@@ -426,7 +439,7 @@ class CACGMMTrainer:
 
 def cacgmm_m_step(y, quadratic_form, affiliation, *, saliency=None,
                   hermitize=True, covariance_norm='eigenvalue',
-                  eigenvalue_floor=1e-10, weight_constant_axis=(-1,)):
+                  eigenvalue_floor=1e-10, weight_constant_axis=(-1,), defer=None):
     """One M-step from given affiliations / quadratic forms (``pbb_cacgmm_mstep``).
 
     estimate_mixture_weight (mixture_model_utils.py:133-203) +
@@ -467,7 +480,7 @@ def cacgmm_m_step(y, quadratic_form, affiliation, *, saliency=None,
         _device.ptr(sal), ctypes.byref(opts), _device.ptr(V), _device.ptr(lam),
         _device.ptr(w), _device.ptr(ws), nbytes, _device.ptr(status),
         _device.stream_ptr()), 'pbb_cacgmm_mstep')
-    _status_check(status, 'cacgmm_m_step')
+    _status_check(status, 'cacgmm_m_step', defer)
     if weight_mode == _lib.WEIGHT_CONST:
         weight = np.full([K, 1], 1 / K)
         if not like_numpy:

@@ -237,9 +237,23 @@ def apply_beamforming_vector(vector, mix):
     code = _device.complex_dtype_code(y)
     assert v.shape[-1] < 30, (v.shape, y.shape)
     D, T = y.shape[-2], y.shape[-1]
-    lead = torch.broadcast_shapes(v.shape[:-1], y.shape[:-2])
+    lead = tuple(torch.broadcast_shapes(v.shape[:-1], y.shape[:-2]))
+    ye = y.expand(*lead, D, T)
+    # leading dims over which the mix is only broadcast (e.g. K beamformers applied to ONE STFT): loop over them with
+    # the kernel instead of materialising a copy of the mix per index
+    bdims = [i for i in range(len(lead)) if lead[i] > 1 and ye.stride(i) == 0]
+    if bdims:
+        others = [i for i in range(len(lead)) if i not in bdims]
+        ve = v.expand(*lead, D).permute(*bdims, *others, len(lead))
+        ysmall = ye[tuple(0 if i in bdims else slice(None) for i in range(len(lead)))]
+        bshape = [lead[i] for i in bdims]
+        outs = [apply_beamforming_vector(ve[idx], ysmall) for idx in np.ndindex(*bshape)]
+        out = torch.stack(outs).reshape(*bshape, *[lead[i] for i in others], T)
+        inv = np.argsort(bdims + others).tolist()
+        out = out.permute(*inv, len(lead))
+        return _device.to_host(out.contiguous(), like_numpy)
     vf = v.expand(*lead, D).reshape(-1, D).contiguous()
-    yf = y.expand(*lead, D, T).reshape(-1, D, T).contiguous()
+    yf = ye.reshape(-1, D, T).contiguous()
     F = vf.shape[0]
     out = _device.empty((F, T), torch.complex128)
     lib = _lib.load()

@@ -61,3 +61,13 @@ a = torch.from_numpy(synth.pos_def_hermitian(1539, 8, 8)).cuda(); b = torch.from
 from pb_bss_b200.extraction.linalg import eigh
 ms, _ = timed(lambda: eigh(a)); print(f'eigh 1539 x 8x8: {ms*1e3:.1f} us')
 ms, _ = timed(lambda: E.get_gev_vector(a, b)); print(f'gev  1539 x 8x8: {ms*1e3:.1f} us')
+# coupled EM (section 8 f2): frequency-tied weights and the inline permutation alignment at the C2 shape, 20 iterations
+from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+F, T, D, K, I = 513, 500, 8, 3, 20
+y = torch.from_numpy(synth.structured_stft(F, T, D, K, seed=5)[0]).cuda(); init = torch.from_numpy(synth.init_affiliation(F, K, T)).cuda()
+ms, _ = timed(lambda: CACGMMTrainer().fit(y, initialization=init, iterations=I, weight_constant_axis=(-3,)), reps=3)
+print(f'coupled cACGMM, tied weights (-3,), F=513 T=500 D=8 K=3 I={I}: {ms:.3f} ms = {ms/I:.3f} ms per iteration')
+al = DHTVPermutationAlignment.from_stft_size(1024)
+ms, _ = timed(lambda: CACGMMTrainer().fit(y, initialization=init, iterations=I, weight_constant_axis=(-3,),
+                                          inline_permutation_aligner=al), reps=3)
+print(f'coupled cACGMM, tied weights + inline DHTV alignment, I={I}: {ms:.3f} ms = {ms/I:.3f} ms per iteration')
