@@ -96,6 +96,7 @@ struct CacgmmWorkspace {
   double* ew;
   double* loglik_part;
   double* aff_stage;  // (F, K, T) device copy of host-resident initial affiliations (streamed upload)
+  int* tcount;        // (F) frame split of em_ws_kernel: parts delivered per bin
   size_t bytes;
 };
 
@@ -121,6 +122,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   const size_t o_ew = take((size_t)F * (K > 4 ? K : 4) * sizeof(double) + 64);  // lean kernel: stride 4
   const size_t o_ll = take((size_t)F * max_chunks(T) * sizeof(double));
   const size_t o_aff = take((size_t)F * K * T * sizeof(double));
+  const size_t o_tcount = take((size_t)F * sizeof(int));
   char* b = reinterpret_cast<char*>(base);
   ws.z = b + o_z;
   ws.zs = zs;
@@ -135,6 +137,7 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   ws.ew = reinterpret_cast<double*>(b + o_ew);
   ws.loglik_part = reinterpret_cast<double*>(b + o_ll);
   ws.aff_stage = reinterpret_cast<double*>(b + o_aff);
+  ws.tcount = reinterpret_cast<int*>(b + o_tcount);
   ws.bytes = off;
   return ws;
 }
@@ -420,7 +423,7 @@ static int launch_persistent_generic(Kern kern, int threads, size_t smem, int* c
   PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long grid = (long long)(*cache) * sms - reserve;
   if (grid < 1) grid = 1;
-  const long long tasks = (long long)a.iterations * a.F;
+  const long long tasks = (long long)a.iterations * a.F * (a.tsplit > 1 ? a.tsplit : 1);
   if (grid > tasks) grid = tasks;
   LaunchScope ls(name, st);
   kern<<<(unsigned)grid, threads, smem, st>>>(a);
@@ -433,7 +436,7 @@ template <int D, int K, typename CT>
 static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
   static int cache_full = 0, cache_lean = 0;
   if (full)
-    return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, 32 * (D / 2),
+    return launch_persistent_generic(em_persistent_kernel<D, K, CT, true, 1>, persist_threads(D, K),
                                      sizeof(PersistSmem<D, K, CT>), &cache_full, a, "em_persistent_kernel", st);
   if constexpr (D == 8) {
     // lane = slot variant (em_ls.cuh): one task per SM, 16 compute warps, no barrier in the hot loop
@@ -446,7 +449,7 @@ static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
       return launch_persistent_generic(em_ws_kernel<K, CT>, 256, sizeof(WsSmem<D, K, CT>), &cache_ws, a,
                                        "em_ws_kernel", st);
   }
-  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL>, 32 * (D / 2),
+  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL>, persist_threads(D, K),
                                    sizeof(PersistSmem<D, K, CT>), &cache_lean, a, "em_persistent_kernel", st);
 }
 
@@ -454,7 +457,7 @@ static int launch_persist_t(const PersistArgs& a, bool full, cudaStream_t st) {
 template <int D, int K, typename CT>
 static int launch_persist_cw_t(const PersistArgs& a, cudaStream_t st) {
   static int cache = 0;
-  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL, 1>, 32 * (D / 2),
+  return launch_persistent_generic(em_persistent_kernel<D, K, CT, false, PBB_CTA_FPL, 1>, persist_threads(D, K),
                                    sizeof(PersistSmem<D, K, CT>), &cache, a, "em_persistent_kernel_cw", st);
 }
 template <int D>
@@ -717,6 +720,26 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
         int cap = (int)(1.6 * (2 * sms - kLoadReserve));
         if (const char* e = getenv("PBB_ORDER_CAP")) cap = atoi(e);  // tuning override
         if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
+      }
+    }
+    if (D == 8 && !full && em_kernel_choice() == 1) {
+      // Frame split (em_ws.cuh): with fewer bins than CTA slots the fit is bound by the per-bin dependency chain
+      // (E / M sweep -> update -> publish -> next sweep), so the sweep of one bin is spread over S CTAs.  The partial
+      // sums live behind the final iteration's block of ws.part (one block of max_chunks(T) is used otherwise).
+      int dev = 0, sms = 0;
+      PBB_CUDA(cudaGetDevice(&dev));
+      PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      const int nchunks = (ws.zs + kStageFrames - 1) / kStageFrames;
+      int S = 1;
+      while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= 2LL * sms) S *= 2;
+      if (const char* e = getenv("PBB_TSPLIT")) S = atoi(e);  // tuning override
+      if (S > nchunks) S = nchunks;
+      if (S + 1 > max_chunks(T)) S = 1;
+      if (S > 1) {
+        p.tsplit = S;
+        p.tpart = ws.part + (size_t)F * K * ((size_t)D * D + 1);
+        p.tcount = ws.tcount;
+        PBB_CUDA(cudaMemsetAsync(ws.tcount, 0, (size_t)F * sizeof(int), st));
       }
     }
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;

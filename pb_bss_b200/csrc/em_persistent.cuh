@@ -71,6 +71,9 @@ struct PersistArgs {
   int wait_load;   // streamed upload: the bin's first task waits for flags[bin] >= 0 (stream_load_kernel)
   const int* order;  // optional explicit task order: order[ticket] = bin | iteration << 16 (host-built, api_cacgmm.cu)
   unsigned long long* phase;  // debug: per-phase cycle sums (PBB_PHASE_TIMING builds)
+  int tsplit;      // em_ws_kernel: parts (ranges of ring stages) one EM iteration of a bin is split into, 0 / 1 = none
+  double* tpart;   // (F, tsplit, K, NS + 1) scatter sums per part
+  int* tcount;     // (F) parts delivered so far, zero at launch
 };
 
 // ---- PTX helpers --------------------------------------------------------------
@@ -519,13 +522,14 @@ __device__ __forceinline__ void lean_chunk2_split(SMT& sm, int cb, int g, int st
       cA[k] = sm.cwx[k][lane];
       cB[k] = sm.cwx[k][32 + lane];
     }
+    // A DFMA reading three different registers issues every 3 cycles, one that finds an operand in the reuse cache
+    // every 2 (scripts/microbench/fp64_operands.cu): runs of NSG instructions share gamma / q of one (class, frame)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int i = 0; i < NSG; ++i) {
-        acc[k * NSG + i] = fma(cA[k], psiA[i], acc[k * NSG + i]);
-        acc[k * NSG + i] = fma(cB[k], psiB[i], acc[k * NSG + i]);
-      }
+      for (int i = 0; i < NSG; ++i) acc[k * NSG + i] = fma(cA[k], psiA[i], acc[k * NSG + i]);
+#pragma unroll
+      for (int i = 0; i < NSG; ++i) acc[k * NSG + i] = fma(cB[k], psiB[i], acc[k * NSG + i]);
     }
   }
 }
@@ -572,7 +576,7 @@ __device__ __forceinline__ void softmax_general(const double (&q)[K], const doub
 // General step (runtime group index): M-step-only iteration 0, and the FULL
 // variant (saliency, source activity mask, log-domain softmax).  Frames are
 // masked individually.
-template <int D, int K, typename CT, bool FULL, typename SMT>
+template <int D, int K, typename CT, bool FULL, bool NAMED = false, typename SMT>
 __device__ __forceinline__ void general_chunk(const PersistArgs& a, SMT& sm, int g, int bin,
                                               int st, int t_chunk, int nsteps, int lane, int& buf, bool mstep_only,
                                               bool fast, double (&acc)[K * GroupDims<D>::NSG], double (&sg)[K]) {
@@ -603,7 +607,7 @@ __device__ __forceinline__ void general_chunk(const PersistArgs& a, SMT& sm, int
           for (int i = 0; i < NSG; ++i) pq = fma(cg[k * NS + i], psi[i], pq);
           sm.xq[buf][g][k][lane] = pq;
         }
-        __syncthreads();
+        em_exchange_barrier<D, NAMED>();
         double q[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -830,12 +834,21 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
     PBB_PHU(11);  // coefficient stores
 }
 
+// Threads of a CTA: the D / 2 slot-group warps and, when there are more classes than those, one "update only" warp
+// per class beyond them (D = 6, K = 4: the fourth class had to wait for a whole class update of warp 0, a quarter of
+// the complex Watson chain).  The extra warps follow the control flow, take every CTA-wide barrier, skip the E / M
+// arithmetic (the slot-group warps then exchange on named barrier 1) and update class g in the update phase.
+__host__ __device__ constexpr int persist_extra_warps(int D, int K) { return K > D / 2 ? K - D / 2 : 0; }
+__host__ __device__ constexpr int persist_threads(int D, int K) { return 32 * (D / 2 + persist_extra_warps(D, K)); }
+
 template <int D, int K, typename CT, bool FULL, int FPL, int MODEL = 0>
-__global__ void __launch_bounds__(32 * (D / 2), (FPL == 2 ? (D == 8 ? 2 : (D == 6 ? 2 : 4)) : (D == 8 ? 3 : (D == 6 ? 4 : 6))))
+__global__ void __launch_bounds__(persist_threads(D, K), (FPL == 2 ? (D == 8 ? 2 : (D == 6 ? 2 : 4)) : (D == 8 ? 3 : (D == 6 ? 4 : 6))))
 em_persistent_kernel(const PersistArgs a) {
   using SM = PersistSmem<D, K, CT>;
   using G = GroupDims<D>;
   constexpr int NS = D * D, M = D / 2, NSG = G::NSG;
+  constexpr int XW = persist_extra_warps(D, K);
+  constexpr bool NAMED = XW > 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
@@ -984,7 +997,9 @@ em_persistent_kernel(const PersistArgs a) {
           sm.tick[1] = tnext;
           sm.tick[2] = nbin;
           sm.tick[3] = nit;
-          sm.ready = (!FULL && MODEL == 0 && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
+          // (no model prefetch with update-only warps: they do not take the exchange barriers that order this
+          // store before the read at the next chunk top)
+          sm.ready = (!FULL && MODEL == 0 && XW == 0 && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
         }
       }
       if (g == 0) {
@@ -996,7 +1011,7 @@ em_persistent_kernel(const PersistArgs a) {
           if (nx < total && !(a.wait_load && nxi == 0)) issue_chunk(nxb, 0, chunk_cnt + 1);
         }
       }
-      if (!FULL && lean && last_chunk && nchunks >= 3 && sm.ready) {
+      if (!FULL && XW == 0 && lean && last_chunk && nchunks >= 3 && sm.ready) {
         // prefetch the next task's model into the other buffer (16-byte L2 -> smem copies)
         pf_next = true;
         const int nb = sm.tick[2];
@@ -1013,6 +1028,10 @@ em_persistent_kernel(const PersistArgs a) {
       }
       const int st = chunk_cnt & 1u;
       PBB_PH(1);  // staging / chunk top
+      if (XW > 0 && g >= M) {  // update-only warp: nothing to do until the sums are complete
+        ++chunk_cnt;
+        continue;
+      }
       mbar_wait(&sm.full[st], (chunk_cnt >> 1) & 1u);
       PBB_PH(2);  // TMA wait
       ++chunk_cnt;
@@ -1020,15 +1039,15 @@ em_persistent_kernel(const PersistArgs a) {
       const int nsteps = (min(kStageFrames, zs - t_chunk)) >> 5;
       if (lean) {
         if constexpr (FPL == 2) {
-          lean_chunk2<D, K, CT, MODEL>(sm, cb, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk2<D, K, CT, MODEL, NAMED>(sm, cb, g, st, nsteps >> 1, lane, buf, a.aff_eps, acc, sg);
           if (nsteps & 1) {  // odd tail step of a short last chunk
-            lean_chunk<D, K, CT, MODEL>(sm, cb, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
+            lean_chunk<D, K, CT, MODEL, NAMED>(sm, cb, g, st, 1, lane, buf, a.aff_eps, acc, sg, nsteps - 1);
           }
         } else {
-          lean_chunk<D, K, CT, MODEL>(sm, cb, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
+          lean_chunk<D, K, CT, MODEL, NAMED>(sm, cb, g, st, nsteps, lane, buf, a.aff_eps, acc, sg);
         }
       }
-      else general_chunk<D, K, CT, FULL>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
+      else general_chunk<D, K, CT, FULL, NAMED>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
       PBB_PH(3);  // EM steps
     }
     if (lean && MODEL == 0 && zs > T) {
@@ -1053,7 +1072,7 @@ em_persistent_kernel(const PersistArgs a) {
 
     // ---- reduce the 32 frames of each warp; group g owns slots [g*NSG, (g+1)*NSG) ----
     warp_reduce_halving<K * NSG>(acc, lane);
-    {
+    if (XW == 0 || g < M) {
       int lo, hi;
       reduce_range<K * NSG>(lane, lo, hi);
 #pragma unroll
@@ -1079,7 +1098,7 @@ em_persistent_kernel(const PersistArgs a) {
       for (int i = tid; i < K * (NS + 1); i += blockDim.x) po[i] = (&sm.S[0][0])[i];
     } else {
       // ---- model update, one warp per class -----------------------------------------
-      for (int k = g; k < K; k += M) {
+      for (int k = g; k < K; k += M + XW) {
         double2* A = sm.A[k];
         double* Ad = reinterpret_cast<double*>(A);
         if constexpr (MODEL == 1) {

@@ -19,6 +19,13 @@
 // All hand-overs are shared-memory mbarriers (full/empty pairs); the E-step exchange of the four
 // EM warps is named barrier 1, the updaters meet on named barrier 2.  The per-bin flag release
 // keeps the cross-CTA protocol of em_persistent.cuh.
+//
+// Frame split (PersistArgs::tsplit = S > 1, chosen by the host when there are fewer bins than CTA slots): a task is
+// one EM iteration of one bin over the ring stages [p * nchunks / S, (p + 1) * nchunks / S), S consecutive tickets per
+// (bin, iteration).  Every part leaves its scatter sums in tpart[bin][p]; the part that arrives last (tcount[bin],
+// one atomic per part) adds the S partial sums in the order p = 0 .. S-1 -- so the result does not depend on which
+// CTA that was -- and updates the model as before.  This shortens the per-bin dependency chain (the E / M sweep is
+// the longest link) at the price of one more L2 round trip per iteration.
 #pragma once
 #include "em_persistent.cuh"
 
@@ -78,8 +85,9 @@ struct WsSmem {
   double ld[K];
   alignas(16) double ew[2][4];
   int tab[NS];
-  int desc[2][4];    // per model buffer: bin, iteration (bin < 0: no more tasks)
-  int sdesc[2][4];   // per S buffer: bin, iteration
+  int desc[2][4];    // per model buffer: bin, iteration, part (bin < 0: no more tasks)
+  int sdesc[2][4];   // per S buffer: bin, iteration, part
+  int tlast;         // frame split: this CTA delivered the last part of the iteration
   uint64_t full[kWsStages], empty[kWsStages];
   uint64_t model_full[2], model_empty[2];
   uint64_t s_full[2], s_empty[2];
@@ -96,8 +104,9 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = a.F, T = a.T, zs = a.zs;
-  const int total = a.iterations * F;
   const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
+  const int S = a.tsplit > 1 ? a.tsplit : 1;  // parts per (bin, iteration); the host keeps S <= nchunks
+  const int total = a.iterations * F * S;
   constexpr uint32_t kStageBytes = (uint32_t)(SM::ROWS * kStageFrames * sizeof(CT));
 
   for (int s = tid; s < NS; s += blockDim.x) sm.tab[s] = slot_pack(D, s);
@@ -127,7 +136,8 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
       const int mb = n & 1;
       mbar_wait(&sm.model_full[mb], (n >> 1) & 1u);
       PBB_PH(0);  // wait for the staged model
-      const int bin = sm.desc[mb][0], it = sm.desc[mb][1];
+      const int bin = sm.desc[mb][0], it = sm.desc[mb][1], part = sm.desc[mb][2];
+      const int c0 = part * nchunks / S, c1 = (part + 1) * nchunks / S;
       if (bin < 0) {
         // no more tasks: tell the updaters
         const int sb = n & 1;
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
 #pragma unroll
       for (int k = 0; k < K; ++k) sg[k] = 0.0;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = c0; c < c1; ++c) {
         const int st = chunk_cnt % kWsStages;
         mbar_wait(&sm.full[st], (chunk_cnt / kWsStages) & 1u);
         PBB_PH(2);  // TMA wait
@@ -177,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         ++chunk_cnt;
         PBB_PH(3);  // EM steps
       }
-      if (!mstep_only && zs > T) {
+      if (!mstep_only && zs > T && c1 == nchunks) {
         // the zs - T padded frames of every row behaved like zero observations
         double q1[K], gp[K], cp[K];
 #pragma unroll
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         if (g == 0 && lane == 0) sm.S[sb][k][NS] = v;
 #endif
       }
-      if (g == 0 && lane == 0) { sm.sdesc[sb][0] = bin; sm.sdesc[sb][1] = it; }
+      if (g == 0 && lane == 0) { sm.sdesc[sb][0] = bin; sm.sdesc[sb][1] = it; sm.sdesc[sb][2] = part; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_full[sb]);
       PBB_PH(6);  // hand-over
@@ -245,16 +255,19 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         int t = 0;
         if (lane == 0) t = atomicAdd(a.ticket, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        int bin = -1, it = 0;
+        int bin = -1, it = 0, part = 0;
         if (t < total) {
+          const int tt = t / S;
+          part = t - tt * S;
           if (a.order != nullptr) {
-            const int v = __ldcg(a.order + t);
+            const int v = __ldcg(a.order + tt);
             bin = v & 0xffff;
             it = v >> 16;
           } else {
-            decode_ticket(t, F, a.iterations, a.wave_c, bin, it);
+            decode_ticket(tt, F, a.iterations, a.wave_c, bin, it);
           }
         }
+        const int c0 = part * nchunks / S, ncp = (part + 1) * nchunks / S - c0;  // this task's ring stages
         const bool mstep_only = a.first_is_m && it == 0;
         const bool late_z = mstep_only && a.wait_load;  // streamed upload: the bin may not have arrived yet
         int issued = 0;  // chunks of this task already requested (lane 0)
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
               if (!done) break;
             }
             mbar_expect_tx(&sm.full[st], kStageBytes);
-            bulk_g2s(&sm.zbuf[st][0][0], zbase + ((size_t)bin * nchunks + issued) * (SM::ROWS * kStageFrames),
+            bulk_g2s(&sm.zbuf[st][0][0], zbase + ((size_t)bin * nchunks + c0 + issued) * (SM::ROWS * kStageFrames),
                      kStageBytes, &sm.full[st]);
             ++chunk_cnt;
             ++issued;
@@ -288,13 +301,13 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
         if (bin >= 0 && lane == 0) {
           // the observation does not depend on the model: request what fits into the ring right away, so
           // that the copy overlaps the flag / model round trips below
-          if (!late_z) issue_chunks(nchunks, false);
+          if (!late_z) issue_chunks(ncp, false);
           // dependency: the bin's previous iteration (or its arrival, streamed upload)
           if (mstep_only) {
             if (a.wait_load) while (ld_acquire_gpu(a.flags + bin) < 0) __nanosleep(200);
           } else {
             while (ld_acquire_gpu(a.flags + bin) < it) {
-              issue_chunks(nchunks, false);  // keep the ring filled while the dependency is still executing
+              issue_chunks(ncp, false);  // keep the ring filled while the dependency is still executing
               __nanosleep(40);
             }
           }
@@ -316,16 +329,16 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
             sm.ew[mb][lane] = wk * exp(ldmin - ldk);
           }
         }
-        if (lane == 0) { sm.desc[mb][0] = bin; sm.desc[mb][1] = it; }
+        if (lane == 0) { sm.desc[mb][0] = bin; sm.desc[mb][1] = it; sm.desc[mb][2] = part; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.model_full[mb]);
         if (bin < 0) break;
         if (lane == 0) {
-          issue_chunks(nchunks, true);
+          issue_chunks(ncp, true);
           // Do not take the next ticket too early: with two tickets per CTA in flight the grid holds
           // more tasks than there are bins and most dependencies are still executing.  Wait until the
           // EM warps have ~2 chunks left (enough to hide ticket, flag and model latency).
-          const unsigned x = chunk_cnt - (unsigned)(nchunks >= PBB_WS_LEAD + 1 ? PBB_WS_LEAD + 1 : nchunks);
+          const unsigned x = chunk_cnt - (unsigned)(ncp >= PBB_WS_LEAD + 1 ? PBB_WS_LEAD + 1 : ncp);
           mbar_wait_relaxed(&sm.empty[x % kWsStages], (x / kWsStages) & 1u, 100);
         }
         __syncwarp();
@@ -352,8 +365,38 @@ __global__ void __launch_bounds__(256, 2) em_ws_kernel(const PersistArgs a) {
           if (lane == 0)
             sm.S[sb][k][NS] = (sm.sgp[sb][0][k] + sm.sgp[sb][1][k]) + (sm.sgp[sb][2][k] + sm.sgp[sb][3][k]);
         __syncwarp();
-        if (last_it) asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
+        if (last_it && S == 1) asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
 #endif
+        if (S > 1) {
+          // frame split: leave this part's sums in L2; whoever delivers the last part adds them up in a fixed order
+          const int part = sm.sdesc[sb][2];
+          constexpr int kRow = K * (NS + 1);
+          double* __restrict__ tp = a.tpart + ((size_t)bin * S + part) * kRow;
+          for (int k = u; k < K; k += NU)
+            for (int i = lane; i < NS + 1; i += 32) __stcg(tp + k * (NS + 1) + i, sm.S[sb][k][i]);
+          __threadfence();
+          asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
+          if (u == 0 && lane == 0) {
+            const int old = atomicAdd(a.tcount + bin, 1);
+            __threadfence();
+            sm.tlast = (old + 1 == (it + 1) * S);
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
+          if (!sm.tlast) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.s_empty[sb]);
+            continue;  // (tlast is rewritten behind the next task's first updater barrier: everyone has read it by then)
+          }
+          const double* __restrict__ tb = a.tpart + (size_t)bin * S * kRow;
+          for (int k = u; k < K; k += NU)
+            for (int i = lane; i < NS + 1; i += 32) {
+              double v = __ldcg(tb + k * (NS + 1) + i);
+              for (int q = 1; q < S; ++q) v += __ldcg(tb + (size_t)q * kRow + k * (NS + 1) + i);
+              sm.S[sb][k][i] = v;
+            }
+          __syncwarp();
+          if (last_it) asm volatile("bar.sync 2, %0;" ::"n"(NU * 32) : "memory");
+        }
         if (last_it) {
           // leave the raw sums for cacg_update_kernel (reference-exact eigendecomposition)
           double* __restrict__ po = a.part + (size_t)bin * K * (NS + 1);

@@ -413,6 +413,32 @@ def test_warp_specialised_and_single_role_kernels_agree(tmp_path):
         np.testing.assert_allclose(res['ws'][k], res['ls'][k], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize('S', [2, 3, 4])
+def test_frame_split_of_a_bin_over_several_ctas(monkeypatch, S):
+    """em_ws_kernel with few bins: one EM iteration of a bin is split over S CTAs by ring stage (em_ws.cuh, "frame
+    split").  Whatever S, the result matches the oracle; and it is deterministic (partial sums added in part order)."""
+    import torch
+    from pb_bss_b200.distribution import CACGMMTrainer
+    monkeypatch.setenv('PBB_TSPLIT', str(S))
+    for (F, T, K, I) in ((5, 500, 3, 12), (9, 290, 2, 7), (3, 1100, 4, 5), (2, 129, 3, 4), (1, 512, 3, 6)):
+        y, _ = synth.structured_stft(F, T, 8, K, seed=11)
+        init = synth.init_affiliation(F, K, T, seed=5)
+        ref = O.cacgmm_fit(y, init, I)
+        m = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+        cov_ref = np.einsum('...de,...e,...fe->...df', ref['eigenvectors'], ref['eigenvalues'], ref['eigenvectors'].conj())
+        np.testing.assert_allclose(m.weight, ref['weight'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(m.cacg.covariance, cov_ref, rtol=0, atol=1e-8)
+        m2 = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+        assert np.array_equal(m.cacg.covariance, m2.cacg.covariance) and np.array_equal(m.weight, m2.weight)
+        # pinned host input: streamed upload with an explicit task order
+        mp = CACGMMTrainer().fit(torch.from_numpy(y).pin_memory(), initialization=torch.from_numpy(init).pin_memory(),
+                                 iterations=I)
+        np.testing.assert_allclose(mp.weight.numpy(), m.weight, rtol=0, atol=1e-12)
+    monkeypatch.setenv('PBB_TSPLIT', '1')
+    m1 = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+    np.testing.assert_allclose(m1.cacg.covariance, m.cacg.covariance, rtol=1e-9, atol=1e-12)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
