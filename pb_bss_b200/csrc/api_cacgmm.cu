@@ -142,6 +142,31 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
   return ws;
 }
 
+// Frame split of the persistent kernels (em_ws.cuh, em_persistent.cuh): with fewer bins than CTA slots the fit is
+// bound by the per-bin dependency chain (E / M sweep -> update -> publish -> next sweep), so the sweep of one bin is
+// spread over S CTAs.  The partial sums live behind the final iteration's block of ws.part (the multi-kernel path
+// uses max_chunks(T) blocks there).
+static int setup_frame_split(PersistArgs* p, const CacgmmWorkspace& ws, int F, int T, int D, int K, int ctas_per_sm,
+                             cudaStream_t st) {
+  int dev = 0, sms = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nchunks = (ws.zs + kStageFrames - 1) / kStageFrames;
+  const long long slots = (long long)ctas_per_sm * sms;
+  int S = 1;
+  while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= slots) S *= 2;
+  if (const char* e = getenv("PBB_TSPLIT")) S = atoi(e);  // tuning override
+  if (S > nchunks) S = nchunks;
+  if (S + 1 > max_chunks(T)) S = 1;
+  if (S > 1) {
+    p->tsplit = S;
+    p->tpart = ws.part + (size_t)F * K * ((size_t)D * D + 1);
+    p->tcount = ws.tcount;
+    PBB_CUDA(cudaMemsetAsync(ws.tcount, 0, (size_t)F * sizeof(int), st));
+  }
+  return 0;
+}
+
 // ---- launches ------------------------------------------------------------------
 template <typename CT>
 static int launch_normalize(const void* y, void* z, int F, int T, int D, int swap, int zs, cudaStream_t st) {
@@ -722,26 +747,9 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
         if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
       }
     }
-    if (D == 8 && !full && em_kernel_choice() == 1) {
-      // Frame split (em_ws.cuh): with fewer bins than CTA slots the fit is bound by the per-bin dependency chain
-      // (E / M sweep -> update -> publish -> next sweep), so the sweep of one bin is spread over S CTAs.  The partial
-      // sums live behind the final iteration's block of ws.part (one block of max_chunks(T) is used otherwise).
-      int dev = 0, sms = 0;
-      PBB_CUDA(cudaGetDevice(&dev));
-      PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const int nchunks = (ws.zs + kStageFrames - 1) / kStageFrames;
-      int S = 1;
-      while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= 2LL * sms) S *= 2;
-      if (const char* e = getenv("PBB_TSPLIT")) S = atoi(e);  // tuning override
-      if (S > nchunks) S = nchunks;
-      if (S + 1 > max_chunks(T)) S = 1;
-      if (S > 1) {
-        p.tsplit = S;
-        p.tpart = ws.part + (size_t)F * K * ((size_t)D * D + 1);
-        p.tcount = ws.tcount;
-        PBB_CUDA(cudaMemsetAsync(ws.tcount, 0, (size_t)F * sizeof(int), st));
-      }
-    }
+    if (!(D == 8 && !full && em_kernel_choice() == 0))  // (not in the opt-in em_ls kernel)
+      if ((r = setup_frame_split(&p, ws, F, T, D, K, full ? (D == 8 ? 3 : D == 6 ? 4 : 6) : (D == 4 ? 4 : 2), st)))
+        return r;
     if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
     if (streamed) {
       LoadStream* l = nullptr;
@@ -944,6 +952,7 @@ int pbb_cwmm_fit(const void* y, int dtype, int F, int T, int D, int K, const dou
     p.coef = ws.coef; p.ld = ws.ld; p.w = ws.w; p.ew = ws.ew;
     p.part = ws.part; p.flags = ws.flags; p.ticket = ws.ticket; p.status = status; p.phase = ws.phase;
     p.spline = u.spline;
+    if ((r = setup_frame_split(&p, ws, F, T, D, K, D == 4 ? 4 : 2, st))) return r;
     if ((r = launch_persist_cw(p, D, K, dtype, st))) return r;
 #ifdef PBB_PHASE_TIMING
     {

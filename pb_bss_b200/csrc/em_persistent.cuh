@@ -188,7 +188,7 @@ struct PersistSmem {
   alignas(16) double raw[2][8];  // lean variant: published (sum gamma_k, ld_k), padded to 4 + 4, cp.async target
   uint64_t full[kStages];
   int tab[NS];
-  int tick[4];            // [0] first ticket; [1..3] next ticket, its bin, its iteration
+  int tick[8];            // [0] first ticket; [1..4] next ticket, its bin, iteration, part; [5] frame split: last part
   int ready;              // the next task's model was already published when probed
 };
 
@@ -853,9 +853,17 @@ em_persistent_kernel(const PersistArgs a) {
   SM& sm = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, g = tid >> 5, lane = tid & 31;
   const int F = a.F, T = a.T, zs = a.zs;
-  const int total = a.iterations * F;
   const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
+  // Frame split (see em_ws.cuh): S consecutive tickets per (bin, iteration), part p sweeps the ring stages
+  // [p * nchunks / S, (p + 1) * nchunks / S); the part that arrives last adds the partial sums and updates the model.
+  const int S = a.tsplit > 1 ? a.tsplit : 1;
+  const int total = a.iterations * F * S;
   const CT* __restrict__ zbase = reinterpret_cast<const CT*>(a.z);
+  auto decode = [&](int t, int& b, int& i, int& p) {
+    const int tt = t / S;
+    p = t - tt * S;
+    decode_ticket(tt, F, a.iterations, a.wave_c, b, i);
+  };
 
   for (int s = tid; s < NS; s += blockDim.x) sm.tab[s] = slot_pack(D, s);
   if (tid == 0) {
@@ -865,14 +873,15 @@ em_persistent_kernel(const PersistArgs a) {
   }
   __syncthreads();
   int cur = sm.tick[0];
-  int bin = 0, it = 0;
+  int bin = 0, it = 0, part = 0;
   if (cur < total) {
     if (a.order != nullptr) {
-      const int v = __ldcg(a.order + cur);
+      const int v = __ldcg(a.order + cur / S);
       bin = v & 0xffff;
       it = v >> 16;
+      part = cur % S;
     } else {
-      decode_ticket(cur, F, a.iterations, a.wave_c, bin, it);
+      decode(cur, bin, it, part);
     }
   }
   unsigned chunk_cnt = 0;  // chunks consumed so far by this CTA (ring position)
@@ -890,7 +899,7 @@ em_persistent_kernel(const PersistArgs a) {
   };
   // streamed upload: a bin's observation may not have arrived yet; its first task issues its own
   // first chunk after the arrival flag instead of having it prefetched
-  if (g == 0 && cur < total && !(a.wait_load && it == 0)) issue_chunk(bin, 0, 0);
+  if (g == 0 && cur < total && !(a.wait_load && it == 0)) issue_chunk(bin, part * nchunks / S, 0);
 
 #ifdef PBB_PHASE_TIMING
   long long _tp = clock64();
@@ -902,7 +911,8 @@ em_persistent_kernel(const PersistArgs a) {
   while (cur < total) {
     const bool mstep_only = a.first_is_m && it == 0;
     const bool last_it = it == a.iterations - 1;
-    int tnext = 0, nbin = 0, nit = 0;  // the task after this one (thread 0; decoded a chunk later)
+    const int c0 = part * nchunks / S, c1 = (part + 1) * nchunks / S, ncp = c1 - c0;  // this task's ring stages
+    int tnext = 0, nbin = 0, nit = 0, npart = 0;  // the task after this one (thread 0; decoded a chunk later)
     int oraw = 0;                      // its entry of the explicit order table, in flight
     if (tid == 0) tnext = atomicAdd(a.ticket, 1);
     if (a.wait_load && it == 0) {
@@ -914,7 +924,7 @@ em_persistent_kernel(const PersistArgs a) {
         // the staged rows were written with ordinary stores by another CTA: order them before
         // this CTA's async-proxy (TMA) read
         asm volatile("fence.proxy.async;" ::: "memory");
-        issue_chunk(bin, 0, chunk_cnt);
+        issue_chunk(bin, c0, chunk_cnt);
       }
     }
     if (!mstep_only && !pf) {
@@ -970,25 +980,25 @@ em_persistent_kernel(const PersistArgs a) {
     __syncthreads();  // model staged
     PBB_PH(7);  // task start -> model staged
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = c0; c < c1; ++c) {
       // The stage refilled below was last read in the previous chunk.  In the E+M loops every
       // observation load of a step precedes that step's exchange barrier, so once warp 0 is
       // here all warps are done with it; only the M-step-only loop (no exchange) needs a barrier.
       if (!lean) __syncthreads();
-      const bool last_chunk = c + 1 == nchunks;
+      const bool last_chunk = c + 1 == c1;
       // Thread 0 walks the next ticket through three chunk tops so that neither the ticket atomic
       // nor the flag probe (L2 round trips) is waited for: consume the ticket and issue the probe at
       // chunk n-3, publish both to shared memory at chunk n-2, everybody reads them at chunk n-1.
       if (tid == 0) {
-        const int c_probe = nchunks >= 3 ? nchunks - 3 : -1;
-        const int c_pub = nchunks >= 2 ? nchunks - 2 : 0;
+        const int c_probe = ncp >= 3 ? c1 - 3 : -1;
+        const int c_pub = ncp >= 2 ? c1 - 2 : c0;
         if (a.order != nullptr) {
           // explicit order: ticket (atomic, task start) -> table entry (issued here) -> decoded one chunk
           // top later; no flag probe / model prefetch in this mode
-          if (c == (c_probe >= 0 ? c_probe : c_pub) && tnext < total) oraw = __ldcg(a.order + tnext);
-          if (c == c_pub) { nbin = oraw & 0xffff; nit = oraw >> 16; }
+          if (c == (c_probe >= 0 ? c_probe : c_pub) && tnext < total) oraw = __ldcg(a.order + tnext / S);
+          if (c == c_pub) { nbin = oraw & 0xffff; nit = oraw >> 16; npart = tnext % S; }
         } else if (c == (c_probe >= 0 ? c_probe : c_pub) && tnext < total) {
-          decode_ticket(tnext, F, a.iterations, a.wave_c, nbin, nit);
+          decode(tnext, nbin, nit, npart);
         }
         if (c == c_probe && !FULL && tnext < total && a.order == nullptr) {
           probe = (a.first_is_m && nit == 0) ? -1 : ld_acquire_gpu(a.flags + nbin) - nit;  // >= 0: published
@@ -997,9 +1007,10 @@ em_persistent_kernel(const PersistArgs a) {
           sm.tick[1] = tnext;
           sm.tick[2] = nbin;
           sm.tick[3] = nit;
+          sm.tick[4] = npart;
           // (no model prefetch with update-only warps: they do not take the exchange barriers that order this
           // store before the read at the next chunk top)
-          sm.ready = (!FULL && MODEL == 0 && XW == 0 && nchunks >= 3 && tnext < total && probe >= 0) ? 1 : 0;
+          sm.ready = (!FULL && MODEL == 0 && XW == 0 && ncp >= 3 && tnext < total && probe >= 0) ? 1 : 0;
         }
       }
       if (g == 0) {
@@ -1008,10 +1019,11 @@ em_persistent_kernel(const PersistArgs a) {
         } else {
           const int nx = __shfl_sync(0xffffffffu, tnext, 0);
           const int nxb = __shfl_sync(0xffffffffu, nbin, 0), nxi = __shfl_sync(0xffffffffu, nit, 0);
-          if (nx < total && !(a.wait_load && nxi == 0)) issue_chunk(nxb, 0, chunk_cnt + 1);
+          const int nxp = __shfl_sync(0xffffffffu, npart, 0);
+          if (nx < total && !(a.wait_load && nxi == 0)) issue_chunk(nxb, nxp * nchunks / S, chunk_cnt + 1);
         }
       }
-      if (!FULL && XW == 0 && lean && last_chunk && nchunks >= 3 && sm.ready) {
+      if (!FULL && XW == 0 && lean && last_chunk && ncp >= 3 && sm.ready) {
         // prefetch the next task's model into the other buffer (16-byte L2 -> smem copies)
         pf_next = true;
         const int nb = sm.tick[2];
@@ -1050,7 +1062,7 @@ em_persistent_kernel(const PersistArgs a) {
       else general_chunk<D, K, CT, FULL, NAMED>(a, sm, g, bin, st, t_chunk, nsteps, lane, buf, mstep_only, fast, acc, sg);
       PBB_PH(3);  // EM steps
     }
-    if (lean && MODEL == 0 && zs > T) {
+    if (lean && MODEL == 0 && zs > T && c1 == nchunks) {
       // the zs - T padded frames of every row behaved like zero observations
       double q1[K], gp[K], cp[K];
 #pragma unroll
@@ -1060,7 +1072,7 @@ em_persistent_kernel(const PersistArgs a) {
 #pragma unroll
       for (int k = 0; k < K; ++k) sg[k] -= npad_lane ? gp[k] : 0.0;
     }
-    if (lean && MODEL == 1 && zs > T) {
+    if (lean && MODEL == 1 && zs > T && c1 == nchunks) {
       double q1[K], gp[K], cp[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) q1[k] = 0.0;
@@ -1092,7 +1104,34 @@ em_persistent_kernel(const PersistArgs a) {
     __syncthreads();
     PBB_PH(4);  // reduce
 
-    if (last_it) {
+    bool deliver = true;  // this CTA holds the complete sums of the iteration
+    if (S > 1) {
+      constexpr int kRow = K * (NS + 1);
+      double* __restrict__ tp = a.tpart + ((size_t)bin * S + part) * kRow;
+      for (int i = tid; i < kRow; i += blockDim.x) __stcg(tp + i, (&sm.S[0][0])[i]);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const int old = atomicAdd(a.tcount + bin, 1);
+        __threadfence();
+        sm.tick[5] = (old + 1 == (it + 1) * S);
+      }
+      __syncthreads();
+      deliver = sm.tick[5] != 0;
+      if (deliver) {
+        const double* __restrict__ tb = a.tpart + (size_t)bin * S * kRow;
+        for (int i = tid; i < kRow; i += blockDim.x) {
+          double v = __ldcg(tb + i);
+          for (int q = 1; q < S; ++q) v += __ldcg(tb + (size_t)q * kRow + i);  // fixed order: independent of who is last
+          (&sm.S[0][0])[i] = v;
+        }
+        __syncthreads();
+      }
+    }
+
+    if (!deliver) {
+      // another CTA completes the iteration
+    } else if (last_it) {
       // leave the raw sums for cacg_update_kernel (reference-exact eigendecomposition)
       double* __restrict__ po = a.part + (size_t)bin * K * (NS + 1);
       for (int i = tid; i < K * (NS + 1); i += blockDim.x) po[i] = (&sm.S[0][0])[i];
@@ -1179,6 +1218,7 @@ em_persistent_kernel(const PersistArgs a) {
     cur = sm.tick[1];
     bin = sm.tick[2];
     it = sm.tick[3];
+    part = sm.tick[4];
     pf = pf_next;
     if (pf_next) cb ^= 1;
     // no barrier needed here: tick / ld / S are next written behind later barriers of the next task

@@ -439,6 +439,28 @@ def test_frame_split_of_a_bin_over_several_ctas(monkeypatch, S):
     np.testing.assert_allclose(m1.cacg.covariance, m.cacg.covariance, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize('S', [2, 4])
+@pytest.mark.parametrize('D,K', [(6, 4), (4, 2), (4, 3), (8, 3)])
+@pytest.mark.parametrize('variant', ['lean', 'saliency'])
+def test_frame_split_on_the_single_role_kernel(monkeypatch, S, D, K, variant):
+    """Frame split in em_persistent_kernel (D = 4 / 6, and the full variant with saliency at any D)."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    monkeypatch.setenv('PBB_TSPLIT', str(S))
+    F, T, I = 4, 530, 6
+    y, _ = synth.structured_stft(F, T, D, K, seed=21)
+    init = synth.init_affiliation(F, K, T, seed=3)
+    sal = None
+    if variant == 'saliency':
+        sal = np.random.default_rng(4).uniform(0.2, 1.0, size=(F, T))
+    ref = O.cacgmm_fit(y, init, I, saliency=sal)
+    m = CACGMMTrainer().fit(y, initialization=init, iterations=I, saliency=sal)
+    cov_ref = np.einsum('...de,...e,...fe->...df', ref['eigenvectors'], ref['eigenvalues'], ref['eigenvectors'].conj())
+    np.testing.assert_allclose(m.weight, ref['weight'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(m.cacg.covariance, cov_ref, rtol=0, atol=1e-8)
+    m2 = CACGMMTrainer().fit(y, initialization=init, iterations=I, saliency=sal)
+    assert np.array_equal(m.cacg.covariance, m2.cacg.covariance)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)

@@ -62,6 +62,23 @@ def test_fit_matches_oracle(F, T, D, K, I):
     np.testing.assert_allclose(model.predict(y), O.cwmm_predict(y, ref), rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize('S', [2, 4])
+@pytest.mark.parametrize('F,T,D,K,I', [(5, 600, 6, 4, 6), (3, 515, 8, 3, 5), (4, 300, 4, 2, 5)])
+def test_frame_split_matches_oracle(monkeypatch, S, F, T, D, K, I):
+    """One EM iteration of a bin split over S CTAs (em_persistent.cuh, "frame split"): same model as the oracle."""
+    from pb_bss_b200.distribution import CWMMTrainer
+    monkeypatch.setenv('PBB_TSPLIT', str(S))
+    y, _ = synth.structured_stft(F, T, D, K, seed=F * T)
+    init = synth.init_affiliation(F, K, T, seed=K)
+    ref = O.cwmm_fit(y, init, I)
+    model = CWMMTrainer().fit(y, initialization=init, iterations=I)
+    np.testing.assert_allclose(model.weight, ref['weight'], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(model.complex_watson.concentration, ref['concentration'], rtol=1e-6)
+    np.testing.assert_allclose(cos_similarity(model.complex_watson.mode, ref['mode']), 1, atol=1e-9)
+    again = CWMMTrainer().fit(y, initialization=init, iterations=I)
+    assert np.array_equal(model.complex_watson.mode, again.complex_watson.mode)
+
+
 @pytest.mark.parametrize('D', [4, 6, 8])
 def test_spline_table_reproduces_reference_inverse(D):
     """The device evaluates the B-spline the trainer exports; the exported
