@@ -323,6 +323,11 @@ int pbb_matvec_batched(const void* matrix, const void* vector, int n, int D,
 int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
                                  int F, int D, int T, void* out, void* stream);
 
+/* The same for B beamformers per bin that share ONE mix (the K sources of a separation on one STFT; the reference
+ * broadcasts the mix in its einsum): vector (B, F, D), mix (F, D, T), out (B, F, T).  B, F <= 65535. */
+int pbb_apply_beamforming_vector_shared(const void* vector, const void* mix, int dtype,
+                                        int B, int F, int D, int T, void* out, void* stream);
+
 /* ------------------------------------------------------------------------
  * Frequency permutation alignment (pb_bss/permutation_alignment.py).
  */

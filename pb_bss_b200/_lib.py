@@ -80,6 +80,7 @@ SIGNATURES = {
     'pbb_rank_one_estimate': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_matvec_batched': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'pbb_apply_beamforming_vector': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    'pbb_apply_beamforming_vector_shared': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -171,14 +171,14 @@ int pbb_blind_analytic_normalization(const void* vector, const void* noise_psd, 
   return 0;
 }
 
-int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype, int F, int D, int T, void* out,
-                                 void* stream) {
+static int apply_bf_launch(const void* vector, const void* mix, int dtype, int B, int F, int D, int T, void* out,
+                           void* stream) {
   PBB_CHECK_ARG(vector && mix, 1, "input is null");
   PBB_CHECK_ARG(dtype == PBB_C64 || dtype == PBB_C128, 3, "bad dtype");
-  PBB_CHECK_ARG(F > 0 && D > 0 && T > 0, 4, "bad shape");
+  PBB_CHECK_ARG(B > 0 && B <= 65535 && F > 0 && F <= 65535 && D > 0 && T > 0, 4, "bad shape");
   PBB_CHECK_ARG(out != nullptr, 7, "out is null");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((T + 255) / 256, F);
+  dim3 grid((T + 255) / 256, F, B);
   LaunchScope ls("apply_bf_kernel", st);
   if (dtype == PBB_C128)
     apply_bf_kernel<double2><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(vector),
@@ -190,6 +190,16 @@ int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype,
                                                    reinterpret_cast<double2*>(out));
   PBB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int pbb_apply_beamforming_vector(const void* vector, const void* mix, int dtype, int F, int D, int T, void* out,
+                                 void* stream) {
+  return apply_bf_launch(vector, mix, dtype, 1, F, D, T, out, stream);
+}
+
+int pbb_apply_beamforming_vector_shared(const void* vector, const void* mix, int dtype, int B, int F, int D, int T,
+                                        void* out, void* stream) {
+  return apply_bf_launch(vector, mix, dtype, B, F, D, T, out, stream);
 }
 
 int pbb_rank_one_estimate(const void* vector, const void* covariance, int n, int D, void* out, void* stream) {

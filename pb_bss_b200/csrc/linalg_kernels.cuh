@@ -404,21 +404,23 @@ __global__ void ban_kernel(const double2* __restrict__ vec, const double2* __res
   for (int d = 0; d < D; ++d) out[(size_t)m * D + d] = make_double2(w[d].x * scale, w[d].y * scale);
 }
 
-// ---- apply a beamforming vector: out[f][t] = sum_d conj(w[f][d]) Y[f][d][t] (beamformer.py:572-583)
+// ---- apply a beamforming vector: out[b][f][t] = sum_d conj(w[b][f][d]) Y[f][d][t] (beamformer.py:572-583);
+// blockIdx.z = b runs over beamformers that share one mix (K sources on one STFT), 1 otherwise
 template <typename CT>
 __global__ void apply_bf_kernel(const double2* __restrict__ w, const CT* __restrict__ Y, int F, int D, int T,
                                 double2* __restrict__ out) {
   const int f = blockIdx.y;
+  const size_t bf = (size_t)blockIdx.z * F + f;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   double2 s = make_double2(0.0, 0.0);
   for (int d = 0; d < D; ++d) {
-    const double2 wd = w[(size_t)f * D + d];
+    const double2 wd = w[bf * D + d];
     const double2 y = ld_cplx(Y + ((size_t)f * D + d) * T + t);
     s.x += wd.x * y.x + wd.y * y.y;
     s.y += wd.x * y.y - wd.y * y.x;
   }
-  out[(size_t)f * T + t] = s;
+  out[bf * T + t] = s;
 }
 
 // ---- rank-1 PSD approximations (beamformer_wrapper.py:11-69) ---------------------

@@ -239,19 +239,25 @@ def apply_beamforming_vector(vector, mix):
     D, T = y.shape[-2], y.shape[-1]
     lead = tuple(torch.broadcast_shapes(v.shape[:-1], y.shape[:-2]))
     ye = y.expand(*lead, D, T)
-    # leading dims over which the mix is only broadcast (e.g. K beamformers applied to ONE STFT): loop over them with
-    # the kernel instead of materialising a copy of the mix per index
+    # leading dims over which the mix is only broadcast (K beamformers applied to ONE STFT): the kernel reads the one
+    # mix for every index instead of a materialised copy per index
     bdims = [i for i in range(len(lead)) if lead[i] > 1 and ye.stride(i) == 0]
     if bdims:
+        nb = len(bdims)
         others = [i for i in range(len(lead)) if i not in bdims]
-        ve = v.expand(*lead, D).permute(*bdims, *others, len(lead))
-        ysmall = ye[tuple(0 if i in bdims else slice(None) for i in range(len(lead)))]
-        bshape = [lead[i] for i in bdims]
-        outs = [apply_beamforming_vector(ve[idx], ysmall) for idx in np.ndindex(*bshape)]
-        out = torch.stack(outs).reshape(*bshape, *[lead[i] for i in others], T)
-        inv = np.argsort(bdims + others).tolist()
-        out = out.permute(*inv, len(lead))
-        return _device.to_host(out.contiguous(), like_numpy)
+        bshape, oshape = [lead[i] for i in bdims], [lead[i] for i in others]
+        B, F = int(np.prod(bshape)), int(np.prod(oshape)) if others else 1
+        ve = v.expand(*lead, D).permute(*bdims, *others, len(lead)).reshape(B, F, D).contiguous()
+        ysmall = ye[tuple(0 if i in bdims else slice(None) for i in range(len(lead)))].reshape(F, D, T).contiguous()
+        out = _device.empty((B, F, T), torch.complex128)
+        lib = _lib.load()
+        _lib.check(lib.pbb_apply_beamforming_vector_shared(_device.ptr(ve), _device.ptr(ysmall), code, B, F, D, T,
+                                                           _device.ptr(out), _device.stream_ptr()),
+                   'pbb_apply_beamforming_vector_shared')
+        out = out.reshape(*bshape, *oshape, T)
+        if bdims != list(range(nb)):
+            out = out.permute(*np.argsort(bdims + others).tolist(), len(lead)).contiguous()
+        return _device.to_host(out, like_numpy)
     vf = v.expand(*lead, D).reshape(-1, D).contiguous()
     yf = ye.reshape(-1, D, T).contiguous()
     F = vf.shape[0]

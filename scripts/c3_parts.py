@@ -7,12 +7,14 @@ from pb_bss_b200.distribution import CACGMMTrainer
 from pb_bss_b200.extraction import (apply_beamforming_vector, get_gev_vector, get_power_spectral_density_matrix)
 from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment, apply_mapping
 
-def timed(name, fn, reps=3):
+def timed(name, fn, reps=5):
     out = fn(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps): out = fn()
-    torch.cuda.synchronize()
-    print('%-28s %8.3f ms' % (name, (time.perf_counter() - t0) / reps * 1e3), flush=True)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); out = fn(); torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    print('%-28s %8.3f ms (median of %d, max %.3f)' % (name, ts[len(ts) // 2] * 1e3, reps, ts[-1] * 1e3), flush=True)
     return out
 
 F, T, D, K = 513, 500, 8, 3

@@ -7,12 +7,16 @@ from pb_bss_b200.distribution import CACGMMTrainer, CWMMTrainer
 from pb_bss_b200 import extraction as E
 
 def timed(fn, reps=5):
+    """median over reps of the device time of one call (a single slow rep -- host jitter on a shared box -- does not
+    move it)"""
     fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): out = fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps, out
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], out
 
 # C1
 F, T, D, K, I = 129, 200, 4, 2, 20
