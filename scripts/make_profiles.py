@@ -62,3 +62,58 @@ if os.path.exists(rep):
     bd = subprocess.run([sys.executable, 'scripts/ncu_breakdown.py', rep, '25'], capture_output=True, text=True).stdout
     open(os.path.join(P, f'em_ws_{tag}_source_breakdown.txt'), 'w').write(bd)
     print(json.dumps(m))
+
+# ---- round 2: text pages made on the GPU box (reports too large to bring back) ----
+def _details_trim(path, limit):
+    det = open(path).read()
+    return '\n'.join(l for l in det.splitlines() if l.strip() and not l.strip().startswith(('OPT', 'INF', 'Est.', '---')))[:limit]
+
+def _raw_select(path, want_sub):
+    rows = list(csv.reader(open(path)))
+    rows = [r for r in rows if len(r) > 20]
+    h, u = rows[0], rows[1]
+    out = []
+    for v in rows[2:]:
+        name = v[h.index('Kernel Name')] if 'Kernel Name' in h else '?'
+        out.append('-- ' + name.split('(')[0])
+        for k, uu, x in zip(h, u, v):
+            if any(s in k for s in want_sub):
+                out.append(f'{k:95s} {x:>18s} {uu}')
+    return '\n'.join(out)
+
+WANT = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'issue_stalled_long_scoreboard_per', 'issue_stalled_barrier_per', 'issue_stalled_short_scoreboard_per',
+        'issue_stalled_wait_per', 'issue_stalled_math_pipe', 'issue_stalled_sleeping', 'issue_stalled_membar', 'issue_stalled_branch']
+cwd = os.path.join(G, f'cw_{tag}_details.txt')
+if os.path.exists(cwd):
+    with open(os.path.join(P, f'cw_{tag}_ncu_full.txt'), 'w') as f:
+        f.write('ncu --set full --clock-control none --import-source on -k regex:em_persistent_kernel -c 1 python scripts/one_fit_cw.py 50\n')
+        f.write('one launch = 50 EM iterations of C4 (complex Watson, F=257 T=1000 D=6 K=4, complex128): em_persistent_kernel<6,4,double2,false,2,1>,\n'
+                '4 warps per CTA (3 slot-group warps + 1 update-only warp); captured on NVIDIA B200 via gpurun (numbers under ncu are NOT bench values)\n\n')
+        f.write('== selected raw metrics ==\n' + _raw_select(os.path.join(G, f'cw_{tag}_raw.csv'), WANT) + '\n\n')
+        f.write('== source-level breakdown (scripts/ncu_breakdown.py) ==\n' + open(os.path.join(G, f'cw_{tag}_source_breakdown.txt')).read() + '\n')
+        f.write('== details page ==\n' + _details_trim(cwd, 9000) + '\n')
+pfd = os.path.join(G, f'postfit_{tag}_details.txt')
+if os.path.exists(pfd):
+    with open(os.path.join(P, f'postfit_{tag}_ncu.txt'), 'w') as f:
+        f.write("ncu --set full --clock-control none -k regex:'dhtv_coop_kernel|em_fast_kernel|gev_kernel|apply_bf_kernel' -c 4 python scripts/run_c3.py --iterations 5\n")
+        f.write('the post-fit kernels of the C3 pipeline (predict = em_fast_kernel, DHTV alignment, GEV beamformer, apply), first launch of each;\n'
+                'captured on NVIDIA B200 via gpurun (numbers under ncu are NOT bench values)\n\n')
+        f.write('== selected raw metrics ==\n' + _raw_select(os.path.join(G, f'postfit_{tag}_raw.csv'), WANT) + '\n\n')
+        det = open(pfd).read()
+        # per kernel: header + speed-of-light + launch statistics + occupancy sections only
+        keep, on = [], False
+        for l in det.splitlines():
+            s_ = l.strip()
+            if s_.startswith('void ') or s_.startswith('pbb::') or 'Context 1, Stream' in l:
+                keep.append(l); continue
+            if s_.startswith('Section:'):
+                on = any(k in s_ for k in ('Speed Of Light Throughput', 'Launch Statistics', 'Occupancy', 'Warp State'))
+            if on and s_ and not s_.startswith(('OPT', 'INF', 'Est.', '---')):
+                keep.append(l)
+        f.write('== details page (speed of light, launch statistics, occupancy, warp state) ==\n' + '\n'.join(keep)[:16000] + '\n')
+for name in (f'pytest_gpu_{tag}.txt',):
+    src = os.path.join(G, name)
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(P, name))
