@@ -75,7 +75,7 @@ class CACGMM(_ProbabilisticModel):
         default_factory=ComplexAngularCentralGaussian)
 
     # -- device views of the model ------------------------------------------------
-    def _device_model(self, independent, F):
+    def _device_model(self, independent, F, N=None):
         V = _device.to_device(self.cacg.covariance_eigenvectors, torch.complex128)
         lam = _device.to_device(self.cacg.covariance_eigenvalues, torch.float64)
         K, D = V.shape[-3], V.shape[-1]
@@ -85,6 +85,9 @@ class CACGMM(_ProbabilisticModel):
         if w.shape[-1] != 1:
             # frequency-tied, time-varying weights (1, K, T) of weight_constant_axis=(-3,)
             assert w.dim() == 3 and w.shape[0] == 1 and len(independent) == 1, tuple(w.shape)
+            # the reference broadcasts weight (1, K, T) against the (F, K, N) log-pdf and fails for T != N
+            if N is not None and w.shape[-1] != N:
+                raise ValueError(f'time-varying weight has {w.shape[-1]} frames, the observation {N}')
             return V, lam, w[0].contiguous(), K, _lib.WEIGHT_TIED_TIME
         w = w[..., 0].expand(*independent, K).reshape(F, K).contiguous()
         return V, lam, w, K, _lib.WEIGHT_TIME
@@ -95,7 +98,7 @@ class CACGMM(_ProbabilisticModel):
         yd = _device.to_device(y)
         code = _device.complex_dtype_code(yd)
         independent, F, N, D = _flatten_obs(yd)
-        V, lam, w, K, wmode = self._device_model(independent, F)
+        V, lam, w, K, wmode = self._device_model(independent, F, N)
         assert V.shape[-1] == D, (V.shape, D)
         act = None
         if source_activity_mask is not None:

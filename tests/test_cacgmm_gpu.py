@@ -461,6 +461,19 @@ def test_frame_split_on_the_single_role_kernel(monkeypatch, S, D, K, variant):
     assert np.array_equal(m.cacg.covariance, m2.cacg.covariance)
 
 
+def test_time_varying_weight_needs_matching_frame_count():
+    """weight_constant_axis=(-3,) gives a weight per frame; predicting an observation with another number of frames
+    fails in the reference (broadcast error) and must not read past the weight buffer here."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    y, _ = synth.structured_stft(6, 80, 4, 2, seed=2)
+    m = CACGMMTrainer().fit(y, initialization=synth.init_affiliation(6, 2, 80, seed=1), iterations=3,
+                            weight_constant_axis=(-3,))
+    assert m.predict(y).shape == (6, 2, 80)
+    y2, _ = synth.structured_stft(6, 96, 4, 2, seed=2)
+    with pytest.raises(ValueError, match='frames'):
+        m.predict(y2)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
