@@ -13,5 +13,6 @@ from . import distribution  # noqa: F401
 from . import extraction  # noqa: F401
 from . import permutation_alignment  # noqa: F401
 from . import initializer  # noqa: F401
+from ._device import deferred_status  # noqa: F401
 
 __all__ = ['distribution', 'extraction', 'permutation_alignment', 'initializer']

@@ -3,10 +3,53 @@
 Nothing here computes: tensors are allocated, copied host<->device and handed
 to the library as raw pointers on torch's current CUDA stream.
 """
+import threading
+
 import numpy as np
 import torch
 
 from . import _lib
+
+_scope = threading.local()
+
+
+class deferred_status:
+    """``with deferred_status():`` -- inside the block the device status words of the library calls (non-finite
+    covariances, GEV / eigensolver failures, singular systems) are not read back after every call, because each read
+    synchronises the stream and exposes the launch overhead of everything that follows; they are all read when the
+    block ends, in call order, and the first failing call raises what it would have raised on the spot.  Later calls of
+    the block may then have run on that call's (NaN) output.  For pipelines of CUDA tensors (parallel.py)."""
+
+    def __enter__(self):
+        self.items = []
+        self.prev = getattr(_scope, 'cur', None)
+        _scope.cur = self
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        _scope.cur = self.prev
+        if exc_type is None:
+            self.check()
+        return False
+
+    def check(self):
+        items, self.items = self.items, []
+        for status, on_error in items:
+            s = int(status.item())
+            if s:
+                on_error(s)
+
+
+def check_status(status, on_error):
+    """Read a device status word now (synchronises) or, inside ``deferred_status``, at the end of the block;
+    ``on_error(s)`` raises the call's exception for a non-zero status ``s``."""
+    cur = getattr(_scope, 'cur', None)
+    if cur is not None:
+        cur.items.append((status, on_error))
+        return
+    s = int(status.item())
+    if s:
+        on_error(s)
 
 
 def require_cuda():

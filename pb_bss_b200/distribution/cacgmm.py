@@ -57,15 +57,14 @@ def _flatten_obs(y):
 
 
 def _status_check(status, what, defer=None):
+    def on_error(s):
+        # the reference asserts finiteness at cacg.py:127,326,333
+        raise AssertionError(f'{what}: non-finite covariance / eigenvalues in bin {s - 1}')
     if defer is not None:
         # coupled EM loop: keep the stream full, look at every status word once after the last iteration
         defer.append((status, what))
         return
-    s = int(status.item())  # synchronises the stream
-    if s != 0:
-        # the reference asserts finiteness at cacg.py:127,326,333
-        raise AssertionError(
-            f'{what}: non-finite covariance / eigenvalues in bin {s - 1}')
+    _device.check_status(status, on_error)  # synchronises the stream unless inside _device.deferred_status()
 
 
 @dataclass

@@ -119,9 +119,9 @@ def get_mvdr_vector(atf_vector, noise_psd_matrix):
                             _device.ptr(scratch), _device.ptr(status), _device.stream_ptr()), 'pbb_mvdr')
     # a singular noise PSD matrix takes the reference's np.linalg.lstsq fallback (beamformer.py:251-256) on the
     # device (minimum-norm solution); the status word is only set where that fallback does not exist (D > 40)
-    s = int(status.item())
-    if s:
+    def on_error(s):
         raise np.linalg.LinAlgError(f'get_mvdr_vector: singular noise PSD matrix {s - 1} (D > 40: no lstsq fallback)')
+    _device.check_status(status, on_error)
     return _device.to_host(w.reshape(*lead, D), like_numpy)
 
 
@@ -149,10 +149,10 @@ def get_gev_vector(target_psd_matrix, noise_psd_matrix, force_cython=False,
     lib = _lib.load()
     _lib.check(lib.pbb_gev_batched(_device.ptr(af), _device.ptr(bf), n, D, _device.ptr(w),
                                    _device.ptr(status), _device.stream_ptr()), 'pbb_gev_batched')
-    s = int(status.item())
-    if s:
+    def on_error(s):
         # get_gev_vector.pyx:130-147 / beamformer.py:398-408
         raise ValueError(f'Error for frequency {s - 1}: noise PSD not positive definite or non-finite input')
+    _device.check_status(status, on_error)
     return _device.to_host(w.reshape(*lead, D), like_numpy)
 
 
@@ -184,9 +184,9 @@ def get_mvdr_vector_souden(target_psd_matrix, noise_psd_matrix, ref_channel=None
     _lib.check(lib.pbb_solve_batched(_device.ptr(nf), _device.ptr(tf), n, D, D, 0, _device.ptr(phi),
                                      _device.ptr(status), _device.stream_ptr()), 'pbb_solve_batched')
     # stable_solve (math/solve.py:95-114): singular systems get the minimum-norm (lstsq) solution on the device
-    s = int(status.item())
-    if s:
+    def on_error(s):
         raise np.linalg.LinAlgError(f'get_mvdr_vector_souden: singular noise PSD matrix {s - 1} (D > 40: no lstsq fallback)')
+    _device.check_status(status, on_error)
     mat = _device.empty((n, D, D), torch.complex128)
     num = _device.empty((n, D), torch.complex128)
     den = _device.empty((n, D), torch.complex128)

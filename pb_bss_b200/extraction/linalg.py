@@ -21,9 +21,9 @@ def eigh(a):
     _lib.check(lib.pbb_heig_batched(
         _device.ptr(ad), n, D, _device.ptr(w), _device.ptr(v),
         _device.ptr(status), _device.stream_ptr()), 'pbb_heig_batched')
-    s = int(status.item())
-    if s:
+    def on_error(s):
         raise np.linalg.LinAlgError(f'eigh: non-finite input or no convergence in matrix {s - 1}')
+    _device.check_status(status, on_error)
     return (_device.to_host(w.reshape(*lead, D), like_numpy),
             _device.to_host(v.reshape(*lead, D, D), like_numpy))
 
@@ -47,9 +47,9 @@ def stable_solve(A, B, hermitize=False):
     _lib.check(lib.pbb_solve_batched(
         _device.ptr(ad.reshape(n, D, D).contiguous()), _device.ptr(bd.reshape(n, D, R).contiguous()), n, D, R,
         1 if hermitize else 0, _device.ptr(x), _device.ptr(status), _device.stream_ptr()), 'pbb_solve_batched')
-    s = int(status.item())
-    if s:
+    def on_error(s):
         raise np.linalg.LinAlgError(f'stable_solve: singular matrix {s - 1} (D > 40: no lstsq fallback)')
+    _device.check_status(status, on_error)
     return _device.to_host(x.reshape(*lead, D, R), like_numpy)
 
 

@@ -16,9 +16,13 @@ same code runs over gloo on CPU tensors, which is how the host logic is
 tested).  Without an initialised process group everything degrades to a
 single rank.
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _device
 
 __all__ = ['world', 'bin_shards', 'local_bins', 'all_gather_bins',
            'mean_over_all_bins', 'sharded_separation', 'StageTimer']
@@ -105,7 +109,7 @@ class StageTimer:
 
 def sharded_separation(y_local, initialization_local, F, *, iterations=100,
                        stft_size=None, beamformer='gev', group=None,
-                       trainer_kwargs=None, timer=None):
+                       trainer_kwargs=None, timer=None, defer_status_checks=True):
     """BASELINE.json config 3 on this rank's bin slice.
 
     cACGMM fit + predict on the local bins -> all-gather of the affiliations
@@ -118,6 +122,7 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
     ``model``, ``affiliation`` (aligned, (F_rank, K, T)), the global
     ``mapping`` (K, F), ``vectors`` (F_rank, K, D) and ``enhanced``
     (F_rank, K, T).  ``timer``: optional StageTimer, marked after every stage.
+    ``defer_status_checks``: read the device status words of all stages once at the end (``deferred_status``).
     """
     def mark(name):
         if timer is not None:
@@ -131,36 +136,39 @@ def sharded_separation(y_local, initialization_local, F, *, iterations=100,
     rank, ws = world(group)
     lo, hi = bin_shards(F, ws)[rank]
     assert y_local.shape[0] == hi - lo, (y_local.shape, (lo, hi))
-    model = CACGMMTrainer().fit(y_local, initialization=initialization_local,
-                                iterations=iterations, **(trainer_kwargs or {}))
-    mark('fit')
-    aff_local = model.predict(y_local)                       # (F_rank, K, T)
-    mark('predict')
-    aff = all_gather_bins(aff_local, F, group)               # the one collective
-    mark('all_gather')
-    if stft_size is None:
-        stft_size = 2 * (F - 1)
-    aligner = DHTVPermutationAlignment.from_stft_size(stft_size)
-    mask_kft = aff.permute(1, 0, 2).contiguous()             # (K, F, T)
-    mapping = aligner.calculate_mapping(mask_kft)            # replicated, identical on all ranks
-    aligned = apply_mapping(mask_kft[:, lo:hi].contiguous(), mapping[:, lo:hi].contiguous())
-    aligned = aligned.permute(1, 0, 2).contiguous()          # (F_rank, K, T)
-    mark('dhtv')
-    Y = y_local.transpose(-1, -2).contiguous()               # (F_rank, D, T)
-    psd = get_power_spectral_density_matrix(Y, aligned)      # (F_rank, K, D, D)
-    mark('psd')
-    K = psd.shape[1]
-    total = psd.sum(1, keepdim=True)
-    noise = (total - psd).contiguous()                       # interference + noise per target class
-    if beamformer == 'gev':
-        vectors = get_gev_vector(psd, noise)                 # (F_rank, K, D)
-    elif beamformer == 'mvdr':
-        vectors = get_mvdr_vector(get_pca_vector(psd).permute(1, 0, 2), noise.permute(1, 0, 2, 3).contiguous()
-                                  ).permute(1, 0, 2)
-    else:
-        raise ValueError(beamformer)
-    mark('beamformer')
-    enhanced = apply_beamforming_vector(vectors.permute(1, 0, 2).contiguous(), Y.unsqueeze(0).expand(K, *Y.shape))
-    mark('apply')
-    return dict(model=model, affiliation=aligned, mapping=mapping,
-                vectors=vectors, enhanced=enhanced.permute(1, 0, 2))
+    # the status words of fit / predict / GEV are read once, after the last stage: reading each on the spot would
+    # synchronise the stream three times and expose the launch overhead of everything queued behind the fit
+    with (_device.deferred_status() if defer_status_checks else contextlib.nullcontext()):
+        model = CACGMMTrainer().fit(y_local, initialization=initialization_local,
+                                    iterations=iterations, **(trainer_kwargs or {}))
+        mark('fit')
+        aff_local = model.predict(y_local)                       # (F_rank, K, T)
+        mark('predict')
+        aff = all_gather_bins(aff_local, F, group)               # the one collective
+        mark('all_gather')
+        if stft_size is None:
+            stft_size = 2 * (F - 1)
+        aligner = DHTVPermutationAlignment.from_stft_size(stft_size)
+        mask_kft = aff.permute(1, 0, 2).contiguous()             # (K, F, T)
+        mapping = aligner.calculate_mapping(mask_kft)            # replicated, identical on all ranks
+        aligned = apply_mapping(mask_kft[:, lo:hi].contiguous(), mapping[:, lo:hi].contiguous())
+        aligned = aligned.permute(1, 0, 2).contiguous()          # (F_rank, K, T)
+        mark('dhtv')
+        Y = y_local.transpose(-1, -2).contiguous()               # (F_rank, D, T)
+        psd = get_power_spectral_density_matrix(Y, aligned)      # (F_rank, K, D, D)
+        mark('psd')
+        K = psd.shape[1]
+        total = psd.sum(1, keepdim=True)
+        noise = (total - psd).contiguous()                       # interference + noise per target class
+        if beamformer == 'gev':
+            vectors = get_gev_vector(psd, noise)                 # (F_rank, K, D)
+        elif beamformer == 'mvdr':
+            vectors = get_mvdr_vector(get_pca_vector(psd).permute(1, 0, 2), noise.permute(1, 0, 2, 3).contiguous()
+                                      ).permute(1, 0, 2)
+        else:
+            raise ValueError(beamformer)
+        mark('beamformer')
+        enhanced = apply_beamforming_vector(vectors.permute(1, 0, 2).contiguous(), Y.unsqueeze(0).expand(K, *Y.shape))
+        mark('apply')
+        return dict(model=model, affiliation=aligned, mapping=mapping,
+                    vectors=vectors, enhanced=enhanced.permute(1, 0, 2))

@@ -194,9 +194,10 @@ def _mapping_from_score_matrix(score_matrix, algorithm='optimal'):
     _lib.check(lib.pbb_mapping_from_score_matrix(_device.ptr(sc), n, K, _ALGORITHMS[algorithm],
                                                  _device.ptr(mapping), _device.ptr(status),
                                                  _device.stream_ptr()), 'pbb_mapping_from_score_matrix')
-    if int(status.item()):
+    def on_error(s):
         # message of scipy.optimize.linear_sum_assignment, like the reference (:511-513)
         raise ValueError('score matrix is infeasible')
+    _device.check_status(status, on_error)
     return _device.to_host(mapping.reshape(K, *F), like_numpy)
 
 

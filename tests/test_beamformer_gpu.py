@@ -85,6 +85,31 @@ def test_souden_known_answer():
     np.testing.assert_allclose(w3, [w] * 3)
 
 
+def test_deferred_status_raises_at_the_end_of_the_block():
+    """pb_bss_b200.deferred_status(): status words are read when the block ends (no per-call synchronisation), the
+    first failing call raises its own exception there; outside a block the call raises on the spot."""
+    import torch
+    import pb_bss_b200
+    from pb_bss_b200 import extraction as E
+    D = 4
+    a = torch.from_numpy(synth.pos_def_hermitian(3, D, D, seed=1)).cuda()
+    b = a.clone()
+    b[1] = -torch.eye(D, dtype=torch.complex128)  # not positive definite
+    with pytest.raises(ValueError, match='frequency 1'):
+        E.get_gev_vector(a, b)
+    reached = []
+    with pytest.raises(ValueError, match='frequency 1'):
+        with pb_bss_b200.deferred_status():
+            w = E.get_gev_vector(a, b)       # does not raise here
+            reached.append(tuple(w.shape))
+            E.get_gev_vector(a, a)           # a later, healthy call
+            reached.append('second')
+    assert reached == [(3, D), 'second']
+    with pb_bss_b200.deferred_status():       # nothing wrong: no exception, results as usual
+        w = E.get_gev_vector(a, a)
+    assert torch.isfinite(torch.view_as_real(w)).all()
+
+
 def test_error_paths():
     from pb_bss_b200 import extraction as E
     D = 4
