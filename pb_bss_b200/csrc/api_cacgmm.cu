@@ -154,7 +154,11 @@ static int setup_frame_split(PersistArgs* p, const CacgmmWorkspace& ws, int F, i
   const int nchunks = (ws.zs + kStageFrames - 1) / kStageFrames;
   const long long slots = (long long)ctas_per_sm * sms;
   int S = 1;
-  while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= slots) S *= 2;
+  // a part must keep enough of the sweep to pay for the extra L2 round trip (partials out, counter, partials in,
+  // ~3 us): measured break-even around T D^2 (K + 1) / S ~ 2.4e4 (C1, D = 4, T = 200 loses 10 % with S = 2;
+  // D = 8, T = 500 gains 12 % with S = 4)
+  const long long sweep = (long long)T * D * D * (K + 1);
+  while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= slots && sweep >= 24000LL * 2 * S) S *= 2;
   if (const char* e = getenv("PBB_TSPLIT")) S = atoi(e);  // tuning override
   if (S > nchunks) S = nchunks;
   if (S + 1 > max_chunks(T)) S = 1;
