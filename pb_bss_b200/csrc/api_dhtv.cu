@@ -3,6 +3,7 @@
 // (_ScoreMatrix.multiply, :404-410) and the greedy assignment (:525-553), and
 // apply_mapping (:54-104).  See include/pbb.h.
 #include <cooperative_groups.h>
+#include <cstring>
 
 #include "common.cuh"
 #include "prof.cuh"
@@ -183,6 +184,7 @@ __device__ __forceinline__ void dhtv_assign(double* __restrict__ score, int K, i
 
 #ifdef PBB_PHASE_TIMING
 __device__ unsigned long long g_dhtv_phase[8];
+__device__ unsigned long long g_dhtv_iters;
 #define DH_PH(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long _t = clock64(); g_dhtv_phase[i] += (unsigned long long)(_t - _tp); _tp = _t; } } while (0)
 #else
 #define DH_PH(i) do { } while (0)
@@ -357,6 +359,281 @@ __global__ void __launch_bounds__(32 * kDhtvCoopMaxWarps) dhtv_coop_kernel(
         break;
       }
     }
+  }
+}
+
+// ---- the whole plan in ONE thread-block cluster, features in (distributed) shared memory ----------------------
+// A segment of the reference's plan is ~100 bins wide (stft_size 1024: 20 segments of 100-120 bins, 58 iterations),
+// i.e. K T doubles x 120 = 1.4 MB: it fits into the shared memory of a 16-CTA cluster.  CTA r owns a contiguous run
+// of the segment's bins, keeps their feature rows in its shared memory for all iterations of the segment and writes
+// the permuted rows back once.  Per iteration: local partial sums -> cluster barrier -> reduce-scatter of the
+// centroid over DSMEM (CTA r adds slice r of the C partial sums in rank order and stores it into every CTA's copy)
+// -> cluster barrier -> norms, K^2 scores per owned bin (one warp per score, operands in shared memory), assignment,
+// in-place permutation -> "changed" flags exchanged over DSMEM -> cluster barrier.  Three ~0.2 us cluster barriers
+// per iteration instead of two ~6 us grid barriers, and no L2 round trip inside an iteration.  Same score arithmetic
+// as dhtv_coop_kernel; only the order in which the bins are added into the centroid differs (by owner).
+constexpr int kDhtvClThreads = 512;
+constexpr int kDhtvClMaxLocal = 16;  // bins one CTA may own (static score / permutation tables)
+static_assert(kDhtvClMaxLocal <= kDhtvClThreads / 32, "one warp per owned bin in the assignment");
+
+__device__ __forceinline__ void dhtv_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dhtv_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t dhtv_map_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dhtv_st_remote_u32(uint32_t addr, int v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// KC = number of classes at compile time (2, 3, 4: clean unrolled code), 0 = any K <= 9 at run time
+template <int KC>
+__global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
+    double* __restrict__ feat, const int* __restrict__ plan, int nplan, int Krt, int F, int T,
+    long long* __restrict__ mapping, int metric, int optimal) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = KC > 0 ? KC : Krt;
+  constexpr int KU = KC > 0 ? KC : kDhtvMaxK;  // unroll bound of the per-class loops
+  const int KT = K * T;
+  double* cent = reinterpret_cast<double*>(smem_raw);  // [K][T] centroid (mean, not normalised), complete in every CTA
+  double* part = cent + KT;                            // [K][T] sum over this CTA's bins
+  double* rows = part + KT;                            // [local bin][K][T]
+  __shared__ double cnorm[kDhtvMaxK];
+  __shared__ double score_s[kDhtvClMaxLocal][kDhtvMaxK * kDhtvMaxK];
+  __shared__ long long map_s[kDhtvClMaxLocal][kDhtvMaxK];  // the owned bins' columns of the mapping
+  __shared__ int perm_s[kDhtvClMaxLocal][kDhtvMaxK];
+  __shared__ int ident_s[kDhtvClMaxLocal];
+  __shared__ int dirty_s[kDhtvClMaxLocal];
+  __shared__ int flags_s[16];
+  uint32_t C, r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(C));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const uint32_t flags_a = dhtv_smem_addr(flags_s);
+  // generic pointers into every CTA's partial sum / centroid (ordinary loads and stores: the compiler keeps all the
+  // remote loads of one element in flight)
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const double* rpart[16];
+  double* rcent[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    rpart[c] = cluster.map_shared_rank(part, c < (int)C ? c : 0);
+    rcent[c] = cluster.map_shared_rank(cent, c < (int)C ? c : 0);
+  }
+#ifdef PBB_PHASE_TIMING
+  long long _tp = clock64();
+#endif
+  const int sl = (KT + (int)C - 1) / (int)C;  // centroid slice reduced by one CTA
+  for (int p = 0; p < nplan; ++p) {
+    const int iters = plan[3 * p], start = plan[3 * p + 1], end = plan[3 * p + 2];
+    const int n = end - start, per = (n + (int)C - 1) / (int)C;
+    const int f0 = start + (int)r * per, f1 = min(end, f0 + per);
+    const int nloc = max(0, f1 - f0);
+    // own rows -> shared memory: warp w takes rows (j, k) = w, w + nwarps, ..., four loads per lane in flight
+    for (int jk = warp; jk < nloc * K; jk += nwarps) {
+      const int j = jk / K, k = jk - j * K;
+      const double* __restrict__ src = feat + ((size_t)k * F + f0 + j) * T;
+      double* __restrict__ dst = rows + j * KT + k * T;
+      for (int c0 = 0; c0 < T; c0 += 512) {  // 16 loads per lane in flight: one L2 round trip per 512 frames of a row
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int t = c0 + lane + 32 * q;
+          v[q] = t < T ? __ldcg(src + t) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int t = c0 + lane + 32 * q;
+          if (t < T) dst[t] = v[q];
+        }
+      }
+    }
+    if (tid < nloc * K) map_s[tid / K][tid % K] = __ldcg(mapping + (size_t)(tid % K) * F + f0 + tid / K);
+    if (tid < kDhtvClMaxLocal) dirty_s[tid] = 0;
+    __syncthreads();
+    DH_PH(0);  // segment load
+    const double inv_n = 1.0 / (double)n;
+    for (int it = 0; it < iters; ++it) {
+      for (int i = tid; i < KT; i += blockDim.x) {
+        double s = 0.0;  // owned bins in ascending order; four loads in flight
+        int j = 0;
+        for (; j + 4 <= nloc; j += 4) {
+          const double a0 = rows[j * KT + i], a1 = rows[(j + 1) * KT + i], a2 = rows[(j + 2) * KT + i],
+                       a3 = rows[(j + 3) * KT + i];
+          s += a0; s += a1; s += a2; s += a3;
+        }
+        for (; j < nloc; ++j) s += rows[j * KT + i];
+        part[i] = s;
+      }
+      DH_PH(1);  // local partial sums
+      dhtv_cluster_sync();  // every CTA's partial sum is complete
+      for (int i = (int)r * sl + tid; i < min(KT, ((int)r + 1) * sl); i += blockDim.x) {
+        double v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = c < (int)C ? rpart[c][i] : 0.0;
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s += v[c];  // rank order (the zeros beyond C change nothing)
+        s *= inv_n;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < (int)C) rcent[c][i] = s;
+      }
+      DH_PH(2);  // barrier 1 + reduce-scatter + broadcast
+      dhtv_cluster_sync();  // the centroid is complete in every CTA
+      DH_PH(3);  // cluster barrier 2
+      // cos: ||centroid_k|| by the LAST warps (they have the fewest score items), applied to the scores afterwards --
+      // <x, c / ||c||> = <x, c> / ||c||, one division per score instead of a pass over the centroid
+      if (metric == 1 && warp >= nwarps - K) {
+        const int k = warp - (nwarps - K);
+        double s = 0.0;
+#pragma unroll 4
+        for (int t = lane; t < T; t += 32) { const double c = cent[k * T + t]; s += c * c; }
+        s = warp_sum(s);
+        if (lane == 0) cnorm[k] = fmax(sqrt(s), kTiny);
+      }
+      // scores of every owned bin: one warp per (bin, mask class km) row, all K centroid rows at once (the row is read
+      // once; K independent accumulators).  Per (kr, km): sum over t in ascending order per lane, then the warp
+      // reduction -- the order of the other DHTV kernels.
+      for (int item = warp; item < nloc * K; item += nwarps) {
+        const int j = item / K, km = item - j * K;
+        const double* __restrict__ row = rows + j * KT + km * T;
+        double sacc[KU];
+#pragma unroll
+        for (int kr = 0; kr < KU; ++kr) sacc[kr] = 0.0;
+        if (metric == 2) {
+#pragma unroll 4
+          for (int t = lane; t < T; t += 32) {
+            const double x = row[t];
+#pragma unroll
+            for (int kr = 0; kr < KU; ++kr)
+              if (KC > 0 || kr < K) { const double dlt = x - cent[kr * T + t]; sacc[kr] += dlt * dlt; }
+          }
+        } else {
+#pragma unroll 4
+          for (int t = lane; t < T; t += 32) {
+            const double x = row[t];
+#pragma unroll
+            for (int kr = 0; kr < KU; ++kr)
+              if (KC > 0 || kr < K) sacc[kr] += x * cent[kr * T + t];
+          }
+        }
+#pragma unroll
+        for (int kr = 0; kr < KU; ++kr) {
+          if (KC > 0 || kr < K) {
+            double v = warp_sum(sacc[kr]);
+            if (metric == 2) v = -sqrt(v);
+            if (lane == 0) score_s[j][kr * K + km] = v;
+          }
+        }
+      }
+      __syncthreads();
+      DH_PH(4);  // norms + scores
+      int moved = 0;
+      if (warp < nloc) {
+        // one warp per owned bin (everything in shared memory / registers: the cluster barrier invalidates the L1, a
+        // thread-local array would cost an L2 round trip per line and iteration)
+        const int j = warp;
+        double* sc = score_s[j];
+        int* perm = perm_s[j];
+        if (metric == 1)
+          for (int i = lane; i < K * K; i += 32) sc[i] = sc[i] / cnorm[i / K];
+        __syncwarp();
+        if (optimal) {
+          if (lane == 0) dhtv_assign(sc, K, 1, perm);
+        } else {
+          // greedy (:525-553): K times the largest remaining score, first one in row-major order on ties; the lanes
+          // hold entries lane, lane + 32, lane + 64 (K^2 <= 81)
+          double e[3];
+          bool alive[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int i = lane + 32 * q;
+            alive[q] = i < K * K;
+            e[q] = alive[q] ? sc[i] : 0.0;
+          }
+          for (int round = 0; round < K; ++round) {
+            double bv = 0.0;
+            int bi = 1 << 30;  // no candidate
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              if (alive[q] && (bi == (1 << 30) || e[q] > bv)) { bv = e[q]; bi = lane + 32 * q; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+              // the candidate with the smaller index wins unless the other one is strictly larger (scan order of the
+              // reference: a later entry replaces the best only if it is greater)
+              const bool take = oi != (1 << 30) && (bi == (1 << 30) || (oi < bi ? !(bv > ov) : ov > bv));
+              if (take) { bv = ov; bi = oi; }
+            }
+            const int row = bi / K, col = bi - row * K;
+            if (lane == 0) perm[row] = col;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int i = lane + 32 * q;
+              if (i / K == row || i % K == col) alive[q] = false;
+            }
+          }
+        }
+        __syncwarp();
+        bool ident = true;
+        for (int k = 0; k < K; ++k) ident = ident && perm[k] == k;
+        if (lane == 0) ident_s[j] = ident ? 1 : 0;
+        if (!ident) {
+          const long long m = lane < K ? map_s[j][perm[lane]] : 0;
+          __syncwarp();
+          if (lane < K) map_s[j][lane] = m;
+          if (lane == 0) dirty_s[j] = 1;
+          moved = 1;
+        }
+      }
+      moved = __syncthreads_or(moved);
+      DH_PH(5);  // assignment
+      for (int j = 0; j < nloc; ++j) {
+        if (ident_s[j]) continue;
+        for (int t = tid; t < T; t += blockDim.x) {
+          double v[KU];
+#pragma unroll
+          for (int k = 0; k < KU; ++k) v[k] = (KC > 0 || k < K) ? rows[j * KT + k * T + t] : 0.0;
+#pragma unroll
+          for (int k = 0; k < KU; ++k) {
+            if (KC > 0 || k < K) {
+              const int src = perm_s[j][k];
+              double x = v[0];
+#pragma unroll
+              for (int q = 1; q < KU; ++q) x = src == q ? v[q] : x;  // register select instead of a local array
+              rows[j * KT + k * T + t] = x;
+            }
+          }
+        }
+      }
+      if (tid < (int)C) dhtv_st_remote_u32(dhtv_map_cta(flags_a + 4u * r, (uint32_t)tid), moved);
+      DH_PH(6);  // permutation
+      dhtv_cluster_sync();  // flags of every CTA have arrived; rows / tables of this iteration are final
+      DH_PH(7);  // cluster barrier 3
+#ifdef PBB_PHASE_TIMING
+      if (blockIdx.x == 0 && tid == 0) g_dhtv_iters += 1;
+#endif
+      int any = 0;
+      for (uint32_t c = 0; c < C; ++c) any |= flags_s[c];
+      if (!any) break;  // nothing moved anywhere: the segment has converged (:352-353); uniform over the cluster
+    }
+    // the segment's permuted rows and mapping columns go back to global memory for the owners of the next segment
+    for (int jk = warp; jk < nloc * K; jk += nwarps) {
+      const int j = jk / K, k = jk - j * K;
+      if (!dirty_s[j]) continue;
+      double* __restrict__ dst = feat + ((size_t)k * F + f0 + j) * T;
+      const double* __restrict__ src = rows + j * KT + k * T;
+      for (int t = lane; t < T; t += 32) __stcg(dst + t, src[t]);
+    }
+    if (tid < nloc * K && dirty_s[tid / K]) mapping[(size_t)(tid % K) * F + f0 + tid / K] = map_s[tid / K][tid % K];
+    __threadfence();
+    dhtv_cluster_sync();
   }
 }
 
@@ -536,6 +813,66 @@ int pbb_dhtv_mapping_ex(const double* mask, int K, int F, int T, const int* plan
     int* plan_dev = changed + total_iters + 2;
     unsigned* bar = reinterpret_cast<unsigned*>(changed + total_iters + 1);  // zeroed with the flags
     PBB_CUDA(cudaMemcpyAsync(plan_dev, plan, (size_t)3 * nplan * sizeof(int), cudaMemcpyHostToDevice, st));
+    int widest_seg = 1;
+    for (int p = 0; p < nplan; ++p)
+      widest_seg = plan[3 * p + 2] - plan[3 * p + 1] > widest_seg ? plan[3 * p + 2] - plan[3 * p + 1] : widest_seg;
+    // Segments that fit into the shared memory of one thread-block cluster (the reference's plans do: ~100 bins):
+    // dhtv_cluster_kernel.  PBB_DHTV_COOP=1 keeps the grid-barrier kernel (A/B).
+    static const bool no_cluster = getenv("PBB_DHTV_COOP") != nullptr;
+    if (!no_cluster) {
+      static int cluster_ctas = -1;  // 16 (non-portable size), 8, or 0 = not available
+      for (int C = cluster_ctas < 0 ? 16 : cluster_ctas; C >= 8; C /= 2) {
+        const int per = (widest_seg + C - 1) / C;
+        const size_t smem = (size_t)(2 + per) * K * T * sizeof(double);
+        if (per > kDhtvClMaxLocal || smem > 200 * 1024) break;
+        using ClusterKern = void (*)(double*, const int*, int, int, int, int, long long*, int, int);
+        const ClusterKern kern = K == 2 ? dhtv_cluster_kernel<2> : K == 3 ? dhtv_cluster_kernel<3>
+                                 : K == 4 ? dhtv_cluster_kernel<4> : dhtv_cluster_kernel<0>;
+        PBB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (C > 8) PBB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(C);
+        cfg.blockDim = dim3(kDhtvClThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cluster_ctas < 0) {
+          int nclusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+            (void)cudaGetLastError();
+            if (C == 8) cluster_ctas = 0;
+            continue;  // try the portable size
+          }
+          cluster_ctas = C;
+        }
+        LaunchScope ls("dhtv_cluster_kernel", st);
+        const int* plan_c = plan_dev;
+        PBB_CUDA(cudaLaunchKernelEx(&cfg, kern, features, plan_c, nplan, K, F, T, mapping, metric, algorithm));
+#ifdef PBB_PHASE_TIMING
+        {
+          unsigned long long ph[8], zero[8] = {0};
+          cudaStreamSynchronize(st);
+          cudaMemcpyFromSymbol(ph, g_dhtv_phase, sizeof(ph));
+          cudaMemcpyToSymbol(g_dhtv_phase, zero, sizeof(zero));
+          static const char* nm[8] = {"segment load (+store)", "partial sums", "barrier 1 + reduce-scatter", "cluster barrier 2",
+                                      "norms + scores", "assignment", "permutation", "cluster barrier 3"};
+          for (int i = 0; i < 8; ++i) fprintf(stderr, "[dhtv cluster] %-22s %10llu cycles\n", nm[i], ph[i]);
+          unsigned long long its = 0, z = 0;
+          cudaMemcpyFromSymbol(&its, g_dhtv_iters, sizeof(its));
+          cudaMemcpyToSymbol(g_dhtv_iters, &z, sizeof(z));
+          fprintf(stderr, "[dhtv cluster] iterations executed %llu of %d planned\n", its, total_iters);
+        }
+#endif
+        return 0;
+      }
+    }
     const size_t smem = (size_t)K * T * sizeof(double);
     PBB_CUDA(cudaFuncSetAttribute(dhtv_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0, sms = 0;
