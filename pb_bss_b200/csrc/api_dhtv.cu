@@ -368,10 +368,12 @@ __global__ void __launch_bounds__(32 * kDhtvCoopMaxWarps) dhtv_coop_kernel(
 // of the segment's bins, keeps their feature rows in its shared memory for all iterations of the segment and writes
 // the permuted rows back once.  Per iteration: local partial sums -> cluster barrier -> reduce-scatter of the
 // centroid over DSMEM (CTA r adds slice r of the C partial sums in rank order and stores it into every CTA's copy)
-// -> cluster barrier -> norms, K^2 scores per owned bin (one warp per score, operands in shared memory), assignment,
-// in-place permutation -> "changed" flags exchanged over DSMEM -> cluster barrier.  Three ~0.2 us cluster barriers
-// per iteration instead of two ~6 us grid barriers, and no L2 round trip inside an iteration.  Same score arithmetic
-// as dhtv_coop_kernel; only the order in which the bins are added into the centroid differs (by owner).
+// -> cluster barrier -> norms, K^2 scores per owned bin (one warp per (bin, mask class), operands in shared memory),
+// warp-parallel greedy assignment, in-place permutation, "changed" flags exchanged over DSMEM, the partial sums of the
+// next iteration (only where a row moved) -> cluster barrier.  Two cluster barriers per iteration instead of two grid
+// barriers, no L2 round trip and no thread-local array inside an iteration (a cluster barrier invalidates the L1).
+// Same score arithmetic as dhtv_coop_kernel up to <x, c/|c|> = <x, c>/|c|; the bins are added into the centroid by
+// owner.  Mappings are identical on every fixture and A/B input (scripts/ab_dhtv.py).
 constexpr int kDhtvClThreads = 512;
 constexpr int kDhtvClMaxLocal = 16;  // bins one CTA may own (static score / permutation tables)
 static_assert(kDhtvClMaxLocal <= kDhtvClThreads / 32, "one warp per owned bin in the assignment");
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
     __syncthreads();
     DH_PH(0);  // segment load
     const double inv_n = 1.0 / (double)n;
-    for (int it = 0; it < iters; ++it) {
+    auto partial_sums = [&]() {
       for (int i = tid; i < KT; i += blockDim.x) {
         double s = 0.0;  // owned bins in ascending order; four loads in flight
         int j = 0;
@@ -469,8 +471,11 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
         for (; j < nloc; ++j) s += rows[j * KT + i];
         part[i] = s;
       }
-      DH_PH(1);  // local partial sums
-      dhtv_cluster_sync();  // every CTA's partial sum is complete
+    };
+    if (iters > 0) partial_sums();
+    DH_PH(1);  // local partial sums
+    dhtv_cluster_sync();  // every CTA's partial sum is complete
+    for (int it = 0; it < iters; ++it) {
       for (int i = (int)r * sl + tid; i < min(KT, ((int)r + 1) * sl); i += blockDim.x) {
         double v[16];
 #pragma unroll
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
         for (int c = 0; c < 16; ++c)
           if (c < (int)C) rcent[c][i] = s;
       }
-      DH_PH(2);  // barrier 1 + reduce-scatter + broadcast
+      DH_PH(2);  // reduce-scatter + broadcast
       dhtv_cluster_sync();  // the centroid is complete in every CTA
       DH_PH(3);  // cluster barrier 2
       // cos: ||centroid_k|| by the LAST warps (they have the fewest score items), applied to the scores afterwards --
@@ -614,8 +619,15 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
       }
       if (tid < (int)C) dhtv_st_remote_u32(dhtv_map_cta(flags_a + 4u * r, (uint32_t)tid), moved);
       DH_PH(6);  // permutation
-      dhtv_cluster_sync();  // flags of every CTA have arrived; rows / tables of this iteration are final
-      DH_PH(7);  // cluster barrier 3
+      // the next iteration's partial sum goes in front of the same barrier (only if a row of this CTA moved: it is
+      // a sum over the owned rows, nothing else); everybody is past the reduce-scatter that read the old one
+      if (moved && it + 1 < iters) {
+        __syncthreads();
+        partial_sums();
+      }
+      DH_PH(1);
+      dhtv_cluster_sync();  // flags and partial sums of every CTA have arrived; rows / tables are final
+      DH_PH(7);  // cluster barrier
 #ifdef PBB_PHASE_TIMING
       if (blockIdx.x == 0 && tid == 0) g_dhtv_iters += 1;
 #endif
