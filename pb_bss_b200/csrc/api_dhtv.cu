@@ -501,9 +501,41 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
         s = warp_sum(s);
         if (lane == 0) cnorm[k] = fmax(sqrt(s), kTiny);
       }
-      // scores of every owned bin: one warp per (bin, mask class km) row, all K centroid rows at once (the row is read
-      // once; K independent accumulators).  Per (kr, km): sum over t in ascending order per lane, then the warp
-      // reduction -- the order of the other DHTV kernels.
+      // scores of every owned bin.  Per (kr, km): sum over t in ascending order per lane, then the warp reduction --
+      // the order of the other DHTV kernels.  The pass is bound by shared-memory bandwidth, so for K <= 4 one warp
+      // takes a whole bin (K feature rows and K centroid rows read once, K^2 accumulators); the generic kernel takes
+      // one (bin, mask class) row per warp with K accumulators.
+      if constexpr (KC > 0) {
+        for (int j = warp; j < nloc; j += nwarps) {
+          const double* __restrict__ rowj = rows + j * KT;
+          double sacc[KC][KC];
+#pragma unroll
+          for (int kr = 0; kr < KC; ++kr)
+#pragma unroll
+            for (int km = 0; km < KC; ++km) sacc[kr][km] = 0.0;
+#pragma unroll 2
+          for (int t = lane; t < T; t += 32) {
+            double x[KC], c[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) { x[k] = rowj[k * T + t]; c[k] = cent[k * T + t]; }
+#pragma unroll
+            for (int kr = 0; kr < KC; ++kr)
+#pragma unroll
+              for (int km = 0; km < KC; ++km) {
+                if (metric == 2) { const double dlt = x[km] - c[kr]; sacc[kr][km] += dlt * dlt; }
+                else sacc[kr][km] += x[km] * c[kr];
+              }
+          }
+#pragma unroll
+          for (int kr = 0; kr < KC; ++kr)
+#pragma unroll
+            for (int km = 0; km < KC; ++km) {
+              double v = warp_sum(sacc[kr][km]);
+              if (metric == 2) v = -sqrt(v);
+              if (lane == 0) score_s[j][kr * KC + km] = v;
+            }
+        }
+      } else {
       for (int item = warp; item < nloc * K; item += nwarps) {
         const int j = item / K, km = item - j * K;
         const double* __restrict__ row = rows + j * KT + km * T;
@@ -516,7 +548,7 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
             const double x = row[t];
 #pragma unroll
             for (int kr = 0; kr < KU; ++kr)
-              if (KC > 0 || kr < K) { const double dlt = x - cent[kr * T + t]; sacc[kr] += dlt * dlt; }
+              if (kr < K) { const double dlt = x - cent[kr * T + t]; sacc[kr] += dlt * dlt; }
           }
         } else {
 #pragma unroll 4
@@ -524,17 +556,18 @@ __global__ void __launch_bounds__(kDhtvClThreads, 1) dhtv_cluster_kernel(
             const double x = row[t];
 #pragma unroll
             for (int kr = 0; kr < KU; ++kr)
-              if (KC > 0 || kr < K) sacc[kr] += x * cent[kr * T + t];
+              if (kr < K) sacc[kr] += x * cent[kr * T + t];
           }
         }
 #pragma unroll
         for (int kr = 0; kr < KU; ++kr) {
-          if (KC > 0 || kr < K) {
+          if (kr < K) {
             double v = warp_sum(sacc[kr]);
             if (metric == 2) v = -sqrt(v);
             if (lane == 0) score_s[j][kr * K + km] = v;
           }
         }
+      }
       }
       __syncthreads();
       DH_PH(4);  // norms + scores

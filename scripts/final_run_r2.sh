@@ -20,7 +20,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:em_p
 ncu -i /tmp/cw_r2.ncu-rep --page details > gpurun_out/cw_r2_details.txt 2>&1
 ncu -i /tmp/cw_r2.ncu-rep --page raw --csv > gpurun_out/cw_r2_raw.csv 2>&1
 python scripts/ncu_breakdown.py /tmp/cw_r2.ncu-rep 25 > gpurun_out/cw_r2_source_breakdown.txt 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:'dhtv_coop_kernel|em_fast_kernel|gev_kernel|apply_bf_kernel' -c 4 -o /tmp/postfit_r2 -f python scripts/run_c3.py --iterations 5 > gpurun_out/ncu_postfit_r2.log 2>&1; tail -2 gpurun_out/ncu_postfit_r2.log
+timeout 600 ncu --set full --clock-control none -k regex:'dhtv_cluster_kernel|em_fast_kernel|gev_kernel|apply_bf_kernel' -c 4 -o /tmp/postfit_r2 -f python scripts/run_c3.py --iterations 5 > gpurun_out/ncu_postfit_r2.log 2>&1; tail -2 gpurun_out/ncu_postfit_r2.log
 ncu -i /tmp/postfit_r2.ncu-rep --page details > gpurun_out/postfit_r2_details.txt 2>&1
 ncu -i /tmp/postfit_r2.ncu-rep --page raw --csv > gpurun_out/postfit_r2_raw.csv 2>&1
 ls -la gpurun_out

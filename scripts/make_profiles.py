@@ -97,7 +97,7 @@ if os.path.exists(cwd):
 pfd = os.path.join(G, f'postfit_{tag}_details.txt')
 if os.path.exists(pfd):
     with open(os.path.join(P, f'postfit_{tag}_ncu.txt'), 'w') as f:
-        f.write("ncu --set full --clock-control none -k regex:'dhtv_coop_kernel|em_fast_kernel|gev_kernel|apply_bf_kernel' -c 4 python scripts/run_c3.py --iterations 5\n")
+        f.write("ncu --set full --clock-control none -k regex:'dhtv_cluster_kernel|em_fast_kernel|gev_kernel|apply_bf_kernel' -c 4 python scripts/run_c3.py --iterations 5\n")
         f.write('the post-fit kernels of the C3 pipeline (predict = em_fast_kernel, DHTV alignment, GEV beamformer, apply), first launch of each;\n'
                 'captured on NVIDIA B200 via gpurun (numbers under ncu are NOT bench values)\n\n')
         f.write('== selected raw metrics ==\n' + _raw_select(os.path.join(G, f'postfit_{tag}_raw.csv'), WANT) + '\n\n')

@@ -19,4 +19,9 @@ CACGMMTrainer().fit(yp, initialization=ip, iterations=4)
 for K in (2, 4):
     yk, _ = synth.structured_stft(9, 200, 8, K, seed=4); ik = synth.init_affiliation(9, K, 200)
     CACGMMTrainer().fit(yk, initialization=ik, iterations=3)
+# DHTV alignment: thread-block-cluster kernel (DSMEM) on a small plan, and the grid-barrier kernel's input range
+from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
+mask = m.predict(y)  # (F, K, T) numpy
+al = DHTVPermutationAlignment(stft_size=22, segment_start=3, segment_width=6, segment_shift=2, main_iterations=4, sub_iterations=2)
+al.calculate_mapping(np.ascontiguousarray(mask.transpose(1, 0, 2)))
 print('ok')
