@@ -21,7 +21,8 @@ for K in (2, 4):
     CACGMMTrainer().fit(yk, initialization=ik, iterations=3)
 # DHTV alignment: thread-block-cluster kernel (DSMEM) on a small plan, and the grid-barrier kernel's input range
 from pb_bss_b200.permutation_alignment import DHTVPermutationAlignment
-mask = m.predict(y)  # (F, K, T) numpy
-al = DHTVPermutationAlignment(stft_size=22, segment_start=3, segment_width=6, segment_shift=2, main_iterations=4, sub_iterations=2)
+y13, _ = synth.structured_stft(13, 120, 8, 3, seed=6); i13 = synth.init_affiliation(13, 3, 120)
+mask = CACGMMTrainer().fit(y13, initialization=i13, iterations=3).predict(y13)  # (F, K, T) numpy
+al = DHTVPermutationAlignment(stft_size=24, segment_start=3, segment_width=6, segment_shift=2, main_iterations=4, sub_iterations=2)
 al.calculate_mapping(np.ascontiguousarray(mask.transpose(1, 0, 2)))
 print('ok')
