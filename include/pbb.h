@@ -346,7 +346,9 @@ int pbb_dhtv_mapping(const double* mask, int K, int F, int T, const int* plan,
 /* The same with the reference's options (permutation_alignment.py:133-163): metric 0 = 'multiply' (raw masks, inner
  * product), 1 = 'cos' (the default: features and centroid L2-normalised over time), 2 = 'euclidean' (minus the
  * distance); algorithm 0 = 'greedy', 1 = 'optimal' (brute force over the K! permutations).  The whole plan runs in
- * one cooperative launch (grid-wide barriers between the centroid and the assignment phase of every iteration). */
+ * one launch: a single thread-block cluster that keeps a segment's feature rows in distributed shared memory when the
+ * widest segment fits (<= 16 bins per CTA of a 16- or 8-CTA cluster and <= 200 KB; the reference's plans do), else one
+ * cooperative launch with grid-wide barriers.  The integer mapping is the same on both. */
 int pbb_dhtv_mapping_ex(const double* mask, int K, int F, int T, const int* plan,
                         int nplan, double* features, double* centroid,
                         long long* mapping, int metric, int algorithm, void* stream);
