@@ -14,6 +14,7 @@
 #include "em_persistent.cuh"
 #include "em_ws.cuh"
 #include "em_ls.cuh"
+#include "em_sticky.cuh"
 #include "prof.cuh"
 
 #ifndef PBB_CTA_FPL
@@ -521,6 +522,61 @@ static int launch_persist_d(const PersistArgs& a, int K, int dtype, bool full, c
   }
 }
 
+// "Sticky bins" (em_sticky.cuh): with F * S <= 2 x SMs a cluster of S CTAs keeps one bin for the whole fit.  S = the
+// largest of 4, 2, 1 whose parts fit the ring (ceil(nchunks / S) <= kWsStages) and that leaves every part a stage.
+// PBB_STICKY=0 disables it, PBB_STICKY=S forces a cluster size (A/B).
+template <int K, typename CT>
+static int launch_sticky_t(const PersistArgs& a, int S, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(WsSmem<8, K, CT>);
+  if (!attr_set) {
+    PBB_CUDA(cudaFuncSetAttribute(em_sticky_kernel<K, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(a.F * S));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LaunchScope ls("em_sticky_kernel", st);
+  PBB_CUDA(cudaLaunchKernelEx(&cfg, em_sticky_kernel<K, CT>, a));
+  return 0;
+}
+static int launch_sticky(const PersistArgs& a, int K, int dtype, int zs, bool* used, cudaStream_t st) {
+  *used = false;
+  int force = -1;
+  if (const char* e = getenv("PBB_STICKY")) force = atoi(e);
+  if (force == 0) return 0;
+  int dev = 0, sms = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
+  int S = 0;
+  for (int c = 4; c >= 1; c /= 2) {
+    if (force > 0 && c != force) continue;
+    if (c > nchunks || (nchunks + c - 1) / c > kWsStages) continue;
+    if ((long long)a.F * c > 2LL * sms) continue;
+    S = c;
+    break;
+  }
+  if (S == 0) return 0;
+  *used = true;
+  const bool c128 = dtype == PBB_C128;
+  switch (K) {
+    case 2: return c128 ? launch_sticky_t<2, double2>(a, S, st) : launch_sticky_t<2, float2>(a, S, st);
+    case 3: return c128 ? launch_sticky_t<3, double2>(a, S, st) : launch_sticky_t<3, float2>(a, S, st);
+    default: return c128 ? launch_sticky_t<4, double2>(a, S, st) : launch_sticky_t<4, float2>(a, S, st);
+  }
+}
+
 static int launch_persist(const PersistArgs& a, int D, int K, int dtype, bool full, cudaStream_t st) {
   switch (D) {
     case 4: return launch_persist_d<4>(a, K, dtype, full, st);
@@ -751,10 +807,16 @@ int pbb_cacgmm_fit(const void* y, int dtype, int F, int T, int D, int K, const d
         if ((r = streamed_order(F, opt->iterations, c, cap < 1 ? 1 : cap, &p.order))) return r;
       }
     }
-    if (!(D == 8 && !full && em_kernel_choice() == 0))  // (not in the opt-in em_ls kernel)
-      if ((r = setup_frame_split(&p, ws, F, T, D, K, full ? (D == 8 ? 3 : D == 6 ? 4 : 6) : (D == 4 ? 4 : 2), st)))
-        return r;
-    if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
+    bool sticky = false;
+    if (D == 8 && !full && !streamed && em_kernel_choice() == 1) {
+      if ((r = launch_sticky(p, K, dtype, ws.zs, &sticky, st))) return r;  // few bins: one cluster per bin (em_sticky.cuh)
+    }
+    if (!sticky) {
+      if (!(D == 8 && !full && em_kernel_choice() == 0))  // (not in the opt-in em_ls kernel)
+        if ((r = setup_frame_split(&p, ws, F, T, D, K, full ? (D == 8 ? 3 : D == 6 ? 4 : 6) : (D == 4 ? 4 : 2), st)))
+          return r;
+      if ((r = launch_persist(p, D, K, dtype, full, st))) return r;
+    }
     if (streamed) {
       LoadStream* l = nullptr;
       if ((r = get_load_stream(&l))) return r;

@@ -474,6 +474,31 @@ def test_time_varying_weight_needs_matching_frame_count():
         m.predict(y2)
 
 
+@pytest.mark.parametrize('S', [1, 2, 4])
+def test_sticky_bins_kernel_matches_the_task_kernel_bit_for_bit(monkeypatch, S):
+    """em_sticky_kernel (one cluster of S CTAs per bin for the whole fit, few bins) sums the parts in the same order
+    as em_ws_kernel with the frame split S: identical models; and both match the oracle."""
+    from pb_bss_b200.distribution import CACGMMTrainer
+    for (F, T, K, I) in ((5, 350, 3, 12), (3, 128 * S, 2, 6), (7, 300, 4, 5), (2, 383, 3, 1)):
+        if (T + 127) // 128 < S:
+            continue
+        y, _ = synth.structured_stft(F, T, 8, K, seed=31)
+        init = synth.init_affiliation(F, K, T, seed=9)
+        monkeypatch.setenv('PBB_STICKY', str(S))
+        m = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+        monkeypatch.setenv('PBB_STICKY', '0')
+        monkeypatch.setenv('PBB_TSPLIT', str(S))
+        mt = CACGMMTrainer().fit(y, initialization=init, iterations=I)
+        monkeypatch.delenv('PBB_TSPLIT')
+        assert np.array_equal(m.cacg.covariance_eigenvectors, mt.cacg.covariance_eigenvectors)
+        assert np.array_equal(m.cacg.covariance_eigenvalues, mt.cacg.covariance_eigenvalues)
+        assert np.array_equal(m.weight, mt.weight)
+        ref = O.cacgmm_fit(y, init, I)
+        cov_ref = np.einsum('...de,...e,...fe->...df', ref['eigenvectors'], ref['eigenvalues'], ref['eigenvectors'].conj())
+        np.testing.assert_allclose(m.weight, ref['weight'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(m.cacg.covariance, cov_ref, rtol=0, atol=1e-8)
+
+
 def test_argument_errors():
     from pb_bss_b200.distribution import CACGMMTrainer
     y = synth.noise_stft(2, 20, 4)
