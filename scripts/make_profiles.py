@@ -117,3 +117,11 @@ for name in (f'pytest_gpu_{tag}.txt',):
     src = os.path.join(G, name)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, name))
+std = os.path.join(G, f'sticky_{tag}_details.txt')
+if os.path.exists(std):
+    with open(os.path.join(P, f'sticky_{tag}_ncu.txt'), 'w') as f:
+        f.write('ncu --set full --clock-control none -k regex:em_sticky_kernel -c 1 python scripts/one_fit_small.py\n')
+        f.write('one launch = 100 EM iterations of a C3 shard (F=65 T=500 D=8 K=3, complex128): 65 clusters of 4 CTAs, one bin each;\n'
+                'captured on NVIDIA B200 via gpurun (numbers under ncu are NOT bench values)\n\n')
+        f.write('== selected raw metrics ==\n' + _raw_select(os.path.join(G, f'sticky_{tag}_raw.csv'), WANT) + '\n\n')
+        f.write('== details page ==\n' + _details_trim(std, 9000) + '\n')
