@@ -721,7 +721,9 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
                                                   double2* __restrict__ A, double2* __restrict__ V,
                                                   double* __restrict__ lamk, const double* __restrict__ Sk,
                                                   const int* __restrict__ tab, double* __restrict__ ld_out,
-                                                  const int* __restrict__ tabE = nullptr) {
+                                                  const int* __restrict__ tabE = nullptr,
+                                                  double* __restrict__ coef_out = nullptr) {
+  // coef_out: destination of the class's NS slot coefficients instead of a.coef (em_sticky.cuh: shared memory)
   constexpr int NS = D * D;
   double* Ad = reinterpret_cast<double*>(A);
     // L2 round trip issued first, consumed after the inversion
@@ -780,7 +782,8 @@ __device__ __forceinline__ void cacg_update_class(const PersistArgs& a, int bin,
     // on det B in the reference's lambda_max = 1 scale -- take the eigendecomposition path there.
     const bool no_floor = ok && isfinite(tinv) && (tr * tn * tinv * a.eigenvalue_floor < 0.5) &&
                           dead_bin == 0;
-    double* __restrict__ co = LS ? a.coef + (size_t)bin * ls_model_doubles(K) : a.coef + ((size_t)bin * K + k) * NS;
+    double* __restrict__ co = coef_out != nullptr ? coef_out
+                              : LS ? a.coef + (size_t)bin * ls_model_doubles(K) : a.coef + ((size_t)bin * K + k) * NS;
     PBB_PHU(10);  // log det, trace of the inverse, floor test
     if (__any_sync(0xffffffffu, bad)) {
       if (lane == 0) atomicMax(a.status, bin + 1);

@@ -9,8 +9,8 @@
 //     memory for the whole fit (at most kWsStages of them: one TMA bulk copy each, at the start);
 //   * per iteration its four EM warps sweep those frames (the hot loop of em_ws_kernel, unchanged) and leave the
 //     scatter sums in shared memory -> cluster barrier -> the update warps of CTA 0 add the S partial sums in rank
-//     order through DSMEM (bit-reproducible) and update the model (cacg_update_class, unchanged) -> cluster barrier
-//     -> every CTA's EM warps fetch the model and start the next sweep.
+//     order through DSMEM (bit-reproducible), update the model (cacg_update_class, unchanged) and store it into
+//     every CTA's model buffer through DSMEM -> cluster barrier -> every CTA's EM warps start the next sweep.
 // No tickets, no flags, no partial sums through L2, no re-streaming of the observation; the E / M arithmetic, the
 // update and therefore the results are those of em_ws_kernel with the frame split (same summation order over the
 // parts).  The host uses it when F * S CTAs are co-resident-sized (F * S <= 2 x SMs) and a part fits the ring
@@ -131,18 +131,15 @@ __global__ void __launch_bounds__(256, 2) em_sticky_kernel(const PersistArgs a) 
         if (lane == 0) sm.sgp[0][g][k] = v;
       }
       sticky_cluster_sync();  // (1) every part's sums are complete
-      sticky_cluster_sync();  // (2) the new model is in L2
+      sticky_cluster_sync();  // (2) CTA 0 has stored the new model into every CTA's shared memory
       if (it + 1 < a.iterations) {
-        // model of the next iteration: coefficients, weights and ew from the published raw scalars (as the producer
-        // warp of em_ws_kernel does)
-        const double* __restrict__ cf = a.coef + (size_t)bin * K * NS;
-        for (int i = tid; i < K * NS; i += 32 * M) (&sm.coef[0][0][0])[i] = __ldcg(cf + i);
+        // weights and ew from the raw scalars (sum of gamma, log det), as the producer warp of em_ws_kernel does
         if (tid < K) {
-          const double ldk = __ldcg(a.ld + (size_t)bin * 4 + tid);
+          const double ldk = sm.ld[tid];
           double ldmin = ldk;
 #pragma unroll
-          for (int j = 0; j < K; ++j) ldmin = fmin(ldmin, __ldcg(a.ld + (size_t)bin * 4 + j));
-          const double sgam = __ldcg(a.ew + (size_t)bin * 4 + tid);
+          for (int j = 0; j < K; ++j) ldmin = fmin(ldmin, sm.ld[j]);
+          const double sgam = sm.S[1][tid][NS];
           const double wk = a.weight_mode == PBB_WEIGHT_CONST ? 1.0 / K : sgam / (double)T;
           sm.ew[0][tid] = wk * exp(ldmin - ldk);
         }
@@ -180,10 +177,25 @@ __global__ void __launch_bounds__(256, 2) em_sticky_kernel(const PersistArgs a) 
           for (int k = u; k < K; k += NU)
             for (int i = lane; i < NS + 1; i += 32) po[k * (NS + 1) + i] = sm.S[1][k][i];
         } else {
-          for (int k = u; k < K; k += NU)
-            cacg_update_class<D, false>(a, bin, k, K, lane, sm.A[k], sm.V[k], sm.lam[k], sm.S[1][k], sm.tab, &sm.ld[k]);
+          for (int k = u; k < K; k += NU) {
+            // the class model goes to a staging row in this CTA's shared memory, then into every CTA's model buffer
+            // through DSMEM: no L2 round trip between the update and the next sweep
+            cacg_update_class<D, false>(a, bin, k, K, lane, sm.A[k], sm.V[k], sm.lam[k], sm.S[1][k], sm.tab, &sm.ld[k],
+                                        nullptr, &sm.coef[1][k][0]);
+            __syncwarp();
+            const double c0v = sm.coef[1][k][lane], c1v = sm.coef[1][k][lane + 32];
+            const double ldk = sm.ld[k], sgam = sm.S[1][k][NS];
+            for (int p = 0; p < S; ++p) {
+              double* rc = cluster.map_shared_rank(&sm.coef[0][k][0], p);
+              rc[lane] = c0v;
+              rc[lane + 32] = c1v;
+              if (lane == 0 && p != 0) {
+                *cluster.map_shared_rank(&sm.ld[k], p) = ldk;
+                *cluster.map_shared_rank(&sm.S[1][k][NS], p) = sgam;
+              }
+            }
+          }
         }
-        __threadfence();
       }
       sticky_cluster_sync();  // (2)
     }
