@@ -61,7 +61,7 @@ def _inputs(rank):
 # clocks sampler (nvidia-smi in a background thread during the timed region)
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """Streams `nvidia-smi -lms 50` for one GPU while the timed region runs."""
+    """Streams `nvidia-smi -lms 10` for one GPU while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap,power.draw')
@@ -70,12 +70,18 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
+        self.head = b''
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                 '--format=csv,noheader,nounits', '-lms', '50'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            time.sleep(0.15)  # first sample is on its way before the timed region starts
+                 '--format=csv,noheader,nounits', '-lms', '10'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, bufsize=0)
+            # the sampler is running before the timed region starts: wait for its first line (nvidia-smi takes a
+            # few hundred ms to come up, longer when eight ranks start one each)
+            import select
+            ready, _, _ = select.select([self.proc.stdout], [], [], 5.0)
+            if ready:
+                self.head = os.read(self.proc.stdout.fileno(), 65536)
         except Exception:
             self.proc = None
         return self
@@ -83,14 +89,15 @@ class ClockSampler:
     def __exit__(self, *a):
         if self.proc is None:
             return
-        time.sleep(0.06)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ''
-        self.rows = [[c.strip() for c in line.split(',')] for line in out.strip().splitlines() if line.strip()]
+            out = b''
+        text = (self.head + (out or b'')).decode(errors='replace')
+        self.rows = [[c.strip() for c in line.split(',')] for line in text.strip().splitlines() if line.strip()]
 
     def summary(self):
         def num(x):
