@@ -111,6 +111,14 @@ typedef struct pbb_cacgmm_options {
  * per time slot, at most `cap` tasks run per slot; every (bin, it) comes after (bin, it - 1). */
 int pbb_streamed_task_order(int F, int iterations, int arrive, int cap, int* order);
 
+/* Host only: which persistent kernel pbb_cacgmm_fit runs for a device-resident problem on a GPU with `sms` SMs, and
+ * how one EM iteration of a bin is split.  lean = no saliency / activity mask / user-supplied model
+ * and eigenvalue_floor in the product-softmax range; streamed = pinned host input.
+ * *kernel: 0 = em_ws_kernel (task kernel, D = 8), 1 = em_sticky_kernel (one cluster of *split CTAs per bin for the
+ * whole fit), 2 = em_persistent_kernel (D = 4 / 6, full variant); *split = parts per bin-iteration (1 = none).  The
+ * environment overrides of the library (PBB_TSPLIT, PBB_STICKY, PBB_EM_KERNEL) are not applied here. */
+int pbb_em_dispatch(int F, int T, int D, int K, int lean, int streamed, int sms, int* kernel, int* split);
+
 /* Bytes of scratch pbb_cacgmm_fit / _predict need for this problem size. */
 size_t pbb_cacgmm_workspace_bytes(int F, int T, int D, int K);
 

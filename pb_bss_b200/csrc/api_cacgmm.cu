@@ -147,12 +147,11 @@ static CacgmmWorkspace carve(void* base, int F, int T, int D, int K) {
 // bound by the per-bin dependency chain (E / M sweep -> update -> publish -> next sweep), so the sweep of one bin is
 // spread over S CTAs.  The partial sums live behind the final iteration's block of ws.part (the multi-kernel path
 // uses max_chunks(T) blocks there).
-static int setup_frame_split(PersistArgs* p, const CacgmmWorkspace& ws, int F, int T, int D, int K, int ctas_per_sm,
-                             cudaStream_t st) {
-  int dev = 0, sms = 0;
-  PBB_CUDA(cudaGetDevice(&dev));
-  PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int nchunks = (ws.zs + kStageFrames - 1) / kStageFrames;
+// Parts a bin-iteration is split into (pure host logic, unit-tested through pbb_em_dispatch).  force > 0 overrides
+// the choice (PBB_TSPLIT); the result always satisfies 1 <= S <= nchunks and S + 1 <= max_chunks(T).
+static int choose_frame_split(int F, int T, int D, int K, int ctas_per_sm, int sms, int force) {
+  const int zs = (T + 31) / 32 * 32;
+  const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
   const long long slots = (long long)ctas_per_sm * sms;
   int S = 1;
   // a part must keep enough of the sweep to pay for the extra L2 round trip (partials out, counter, partials in,
@@ -160,9 +159,35 @@ static int setup_frame_split(PersistArgs* p, const CacgmmWorkspace& ws, int F, i
   // D = 8, T = 500 gains 12 % with S = 4)
   const long long sweep = (long long)T * D * D * (K + 1);
   while (S < 4 && 2 * S <= nchunks && (long long)F * 2 * S <= slots && sweep >= 24000LL * 2 * S) S *= 2;
-  if (const char* e = getenv("PBB_TSPLIT")) S = atoi(e);  // tuning override
+  if (force > 0) S = force;
   if (S > nchunks) S = nchunks;
   if (S + 1 > max_chunks(T)) S = 1;
+  return S < 1 ? 1 : S;
+}
+// Cluster size of the sticky-bins kernel (em_sticky.cuh), 0 = not applicable: the largest of 4, 2, 1 whose parts fit
+// the ring (ceil(nchunks / S) <= kWsStages), that leaves every part a stage and whose F * S CTAs fit the machine at
+// once (two CTAs per SM).  force: -1 automatic, 0 off, S > 0 only that size (PBB_STICKY).
+static int choose_sticky(int F, int T, int sms, int force) {
+  if (force == 0) return 0;
+  const int zs = (T + 31) / 32 * 32;
+  const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
+  for (int c = 4; c >= 1; c /= 2) {
+    if (force > 0 && c != force) continue;
+    if (c > nchunks || (nchunks + c - 1) / c > kWsStages) continue;
+    if ((long long)F * c > 2LL * sms) continue;
+    return c;
+  }
+  return 0;
+}
+
+static int setup_frame_split(PersistArgs* p, const CacgmmWorkspace& ws, int F, int T, int D, int K, int ctas_per_sm,
+                             cudaStream_t st) {
+  int dev = 0, sms = 0;
+  PBB_CUDA(cudaGetDevice(&dev));
+  PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int force = 0;
+  if (const char* e = getenv("PBB_TSPLIT")) force = atoi(e);  // tuning override
+  const int S = choose_frame_split(F, T, D, K, ctas_per_sm, sms, force);
   if (S > 1) {
     p->tsplit = S;
     p->tpart = ws.part + (size_t)F * K * ((size_t)D * D + 1);
@@ -558,15 +583,8 @@ static int launch_sticky(const PersistArgs& a, int K, int dtype, int zs, bool* u
   int dev = 0, sms = 0;
   PBB_CUDA(cudaGetDevice(&dev));
   PBB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int nchunks = (zs + kStageFrames - 1) / kStageFrames;
-  int S = 0;
-  for (int c = 4; c >= 1; c /= 2) {
-    if (force > 0 && c != force) continue;
-    if (c > nchunks || (nchunks + c - 1) / c > kWsStages) continue;
-    if ((long long)a.F * c > 2LL * sms) continue;
-    S = c;
-    break;
-  }
+  (void)zs;
+  const int S = choose_sticky(a.F, a.T, sms, force);
   if (S == 0) return 0;
   *used = true;
   const bool c128 = dtype == PBB_C128;
@@ -630,6 +648,22 @@ int pbb_normalize_observation(const void* y, void* z, int F, int T, int D, int d
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == PBB_C128 ? launch_normalize<double2>(y, z, F, T, D, swap, T, st)
                            : launch_normalize<float2>(y, z, F, T, D, swap, T, st);
+}
+
+int pbb_em_dispatch(int F, int T, int D, int K, int lean, int streamed, int sms, int* kernel, int* split) {
+  PBB_CHECK_ARG(F > 0, 1, "F must be positive");
+  PBB_CHECK_ARG(T > 0, 2, "T must be positive");
+  PBB_CHECK_ARG(D == 4 || D == 6 || D == 8, 3, "persistent kernels: D in {4, 6, 8}");
+  PBB_CHECK_ARG(K >= 2 && K <= 4, 4, "persistent kernels: K in {2, 3, 4}");
+  PBB_CHECK_ARG(sms > 0, 7, "sms must be positive");
+  PBB_CHECK_ARG(kernel != nullptr && split != nullptr, 8, "output is null");
+  if (D == 8 && lean && !streamed) {
+    const int S = choose_sticky(F, T, sms, -1);
+    if (S > 0) { *kernel = 1; *split = S; return 0; }
+  }
+  *kernel = (D == 8 && lean) ? 0 : 2;
+  *split = choose_frame_split(F, T, D, K, lean ? (D == 4 ? 4 : 2) : (D == 8 ? 3 : D == 6 ? 4 : 6), sms, 0);
+  return 0;
 }
 
 int pbb_streamed_task_order(int F, int iterations, int arrive, int cap, int* order) {

@@ -105,3 +105,51 @@ def test_streamed_task_order_is_a_valid_schedule(F, I, arrive, cap):
     if cap >= arrive:  # then bins enter in the order in which they arrive
         assert (np.diff(pos[:, 0]) > 0).all()
     assert lib.pbb_streamed_task_order(F, 0, arrive, cap, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == -2
+
+
+def _dispatch(F, T, D, K, lean=1, streamed=0, sms=148):
+    from pb_bss_b200 import _lib
+    lib = _lib.load()
+    kernel, split = ctypes.c_int(-1), ctypes.c_int(-1)
+    rc = lib.pbb_em_dispatch(F, T, D, K, lean, streamed, sms, ctypes.byref(kernel), ctypes.byref(split))
+    assert rc == 0, lib.pbb_last_error()
+    return kernel.value, split.value
+
+
+def test_em_kernel_dispatch_for_the_benchmark_configs():
+    """Host logic of pbb_cacgmm_fit's kernel choice (api_cacgmm.cu: choose_sticky / choose_frame_split) on a 148-SM
+    GPU: 0 = task kernel em_ws, 1 = sticky bins (one cluster per bin), 2 = single-role persistent kernel."""
+    assert _dispatch(513, 500, 8, 3) == (0, 1)                 # C2: more bins than CTA slots
+    assert _dispatch(257, 500, 8, 3) == (0, 1)                 # C3, 2 ranks: 4 ring stages per bin do not fit one CTA
+    assert _dispatch(129, 500, 8, 3) == (1, 2)                 # C3, 4 ranks
+    assert _dispatch(65, 500, 8, 3) == (1, 4)                  # C3, 8 ranks
+    assert _dispatch(65, 500, 8, 3, streamed=1) == (0, 4)      # pinned host input: task kernel with the frame split
+    assert _dispatch(129, 200, 4, 2) == (2, 1)                 # C1: the sweep is too short to split
+    assert _dispatch(257, 1000, 6, 4) == (2, 1)                # C4
+    assert _dispatch(65, 1000, 6, 4) == (2, 4)
+    assert _dispatch(40, 500, 8, 3, lean=0) == (2, 4)          # saliency / masks: full variant
+    assert _dispatch(64, 1100, 8, 3) == (1, 4)                 # 9 ring stages: 3 per CTA
+    assert _dispatch(10, 2000, 8, 3) == (0, 4)                 # 16 stages: a part does not fit the ring of a sticky CTA
+    assert _dispatch(5, 100, 8, 2) == (1, 1)                   # one ring stage: nothing to split
+
+
+def test_em_kernel_dispatch_invariants():
+    from pb_bss_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        F, T = int(rng.integers(1, 2000)), int(rng.integers(2, 3000))
+        D, K = int(rng.choice([4, 6, 8])), int(rng.integers(2, 5))
+        lean, streamed, sms = int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.choice([16, 132, 148]))
+        kernel, S = _dispatch(F, T, D, K, lean, streamed, sms)
+        nchunks = ((T + 31) // 32 * 32 + 127) // 128
+        assert 1 <= S <= max(1, nchunks) and S in (1, 2, 4)
+        if kernel == 1:
+            assert D == 8 and lean and not streamed and F * S <= 2 * sms and -(-nchunks // S) <= 3
+        elif kernel == 0:
+            assert D == 8 and lean
+        else:
+            assert kernel == 2 and (D != 8 or not lean)
+    k, s_ = ctypes.c_int(), ctypes.c_int()
+    assert lib.pbb_em_dispatch(0, 10, 8, 3, 1, 0, 148, ctypes.byref(k), ctypes.byref(s_)) == -1
+    assert lib.pbb_em_dispatch(5, 10, 5, 3, 1, 0, 148, ctypes.byref(k), ctypes.byref(s_)) == -3
