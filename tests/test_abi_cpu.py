@@ -153,3 +153,41 @@ def test_em_kernel_dispatch_invariants():
     k, s_ = ctypes.c_int(), ctypes.c_int()
     assert lib.pbb_em_dispatch(0, 10, 8, 3, 1, 0, 148, ctypes.byref(k), ctypes.byref(s_)) == -1
     assert lib.pbb_em_dispatch(5, 10, 5, 3, 1, 0, 148, ctypes.byref(k), ctypes.byref(s_)) == -3
+
+
+def test_deferred_status_scope_host_logic():
+    """_device.deferred_status / check_status with plain CPU tensors as status words: immediate raise outside a block,
+    one read per word at the end of the block in call order, nesting, and no masking of an exception raised inside."""
+    import torch
+    from pb_bss_b200 import _device
+
+    def raiser(tag):
+        def on_error(s):
+            raise ValueError(f'{tag}:{s}')
+        return on_error
+
+    ok, bad3, bad7 = torch.zeros(1, dtype=torch.int32), torch.tensor([3], dtype=torch.int32), torch.tensor([7], dtype=torch.int32)
+    _device.check_status(ok, raiser('a'))                       # nothing to report
+    with pytest.raises(ValueError, match='b:3'):
+        _device.check_status(bad3, raiser('b'))                 # outside a block: on the spot
+    seen = []
+    with pytest.raises(ValueError, match='b:3'):               # the FIRST failing call of the block raises
+        with _device.deferred_status() as scope:
+            _device.check_status(ok, raiser('a'))
+            _device.check_status(bad3, raiser('b'))
+            _device.check_status(bad7, raiser('c'))
+            seen.append(len(scope.items))
+    assert seen == [3]
+    with _device.deferred_status() as outer:                    # nested blocks: the inner one reports at its own end
+        with pytest.raises(ValueError, match='c:7'):
+            with _device.deferred_status():
+                _device.check_status(bad7, raiser('c'))
+        _device.check_status(ok, raiser('a'))
+        assert len(outer.items) == 1
+    with pytest.raises(KeyError):                               # an exception from the body is not replaced
+        with _device.deferred_status():
+            _device.check_status(bad3, raiser('b'))
+            raise KeyError('body')
+    _device.check_status(ok, raiser('a'))                       # and the scope is gone afterwards
+    with pytest.raises(ValueError, match='b:3'):
+        _device.check_status(bad3, raiser('b'))
