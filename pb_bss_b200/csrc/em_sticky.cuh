@@ -22,6 +22,13 @@
 
 namespace pbb {
 
+#ifndef PBB_STICKY_EM_REGS
+// Register budget of the EM warps (the helpers get 256 - this), multiple of 8.  200 / 56 instead of em_ws_kernel's
+// 208 / 48: the update warps spill less, and a spill reload behind a cluster barrier (which invalidates the L1) is
+// an L2 round trip.  scripts/sticky_regs_ab.py: F = 65: 1.045 -> 1.016 ms, F = 17: 0.949 -> 0.927 ms, same results.
+#define PBB_STICKY_EM_REGS 200
+#endif
+
 __device__ __forceinline__ void sticky_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(256, 2) em_sticky_kernel(const PersistArgs a) 
 
   if (warp < M) {
     // =============================== EM warps ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsEmRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PBB_STICKY_EM_REGS));
     const int g = warp;
     int buf = 0;
 #pragma unroll 1
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) em_sticky_kernel(const PersistArgs a) 
       }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHelperRegs));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(256 - PBB_STICKY_EM_REGS));
     const int u = warp - M - 1;  // updater index (warp M only keeps the barriers company)
 #pragma unroll 1
     for (int it = 0; it < a.iterations; ++it) {
